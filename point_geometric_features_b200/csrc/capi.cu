@@ -1,0 +1,547 @@
+// capi.cu -- the extern "C" boundary declared in include/pgeof_b200.h.
+// Host flavours stage numpy buffers through stream-ordered device scratch; device flavours
+// run directly on the caller's buffers and stream.  No entry point computes on the CPU.
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pgeof {
+
+thread_local uint64_t g_launches = 0;
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------------------
+// device scratch: cudaMallocAsync on the device's default pool, never trimmed
+// ---------------------------------------------------------------------------
+static std::mutex g_pool_mutex;
+static bool g_pool_ready[64] = {};
+
+static int ensure_pool(int device)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (device < 0 || device >= 64 || g_pool_ready[device]) return PGEOF_OK;
+    cudaMemPool_t pool;
+    PGEOF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    PGEOF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    g_pool_ready[device] = true;
+    return PGEOF_OK;
+}
+
+int DeviceBuffer::alloc(size_t bytes, cudaStream_t s)
+{
+    release();
+    stream = s;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? PGEOF_ENOMEM : PGEOF_ECUDA;
+    }
+    return PGEOF_OK;
+}
+
+void DeviceBuffer::release()
+{
+    if (ptr) { cudaFreeAsync(ptr, stream); ptr = nullptr; }
+}
+
+// ---------------------------------------------------------------------------
+// per-thread context: device check + the stream host entry points run on
+// ---------------------------------------------------------------------------
+struct HostCtx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+};
+static thread_local HostCtx g_ctx;
+
+static int ensure_device(int* device_out)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); pgeof_b200 has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        return PGEOF_ECUDA;
+    }
+    int dev = 0;
+    PGEOF_CUDA(cudaGetDevice(&dev));
+    PGEOF_TRY(ensure_pool(dev));
+    if (device_out) *device_out = dev;
+    return PGEOF_OK;
+}
+
+static int host_stream(cudaStream_t* s)
+{
+    int dev = 0;
+    PGEOF_TRY(ensure_device(&dev));
+    if (g_ctx.device != dev || !g_ctx.stream) {
+        if (g_ctx.stream) { cudaSetDevice(g_ctx.device); cudaStreamDestroy(g_ctx.stream); cudaSetDevice(dev); g_ctx.stream = nullptr; }
+        PGEOF_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        g_ctx.device = dev;
+    }
+    *s = g_ctx.stream;
+    return PGEOF_OK;
+}
+
+// Switches to the device that owns `p` for the lifetime of the guard.
+struct DeviceGuard {
+    int prev = -1;
+    int enter(const void* p)
+    {
+        int dev = 0;
+        PGEOF_TRY(ensure_device(&dev));
+        cudaPointerAttributes attr;
+        cudaError_t e = cudaPointerGetAttributes(&attr, p);
+        if (e != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+            cudaGetLastError();
+            set_error("expected a CUDA device pointer");
+            return PGEOF_EINVAL;
+        }
+        if (attr.device != dev) { prev = dev; PGEOF_CUDA(cudaSetDevice(attr.device)); PGEOF_TRY(ensure_pool(attr.device)); }
+        return PGEOF_OK;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------
+// pinned host pool (backs numpy result arrays created by the binding)
+// ---------------------------------------------------------------------------
+struct PinnedPool {
+    std::mutex m;
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;
+    static size_t round(size_t b) { const size_t g = b < ((size_t)1 << 20) ? 4096 : ((size_t)2 << 20); return (b + g - 1) / g * g; }
+    void* get(size_t bytes)
+    {
+        const size_t want = round(bytes ? bytes : 1);
+        std::lock_guard<std::mutex> lock(m);
+        auto it = free_blocks.lower_bound(want);
+        if (it != free_blocks.end() && it->first <= want + want / 4 + 4096) {
+            void* p = it->second; live[p] = it->first; free_blocks.erase(it); return p;
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            trim_locked();
+            if (cudaHostAlloc(&p, want, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        }
+        live[p] = want;
+        return p;
+    }
+    void put(void* p)
+    {
+        std::lock_guard<std::mutex> lock(m);
+        auto it = live.find(p);
+        if (it == live.end()) return;
+        free_blocks.emplace(it->second, p);
+        live.erase(it);
+    }
+    void trim_locked()
+    {
+        for (auto& kv : free_blocks) cudaFreeHost(kv.second);
+        free_blocks.clear();
+    }
+};
+static PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; }   // leaked on purpose (exit order)
+
+// host <-> device staging helpers
+static int h2d(DeviceBuffer* d, const void* h, size_t bytes, cudaStream_t s)
+{
+    PGEOF_TRY(d->alloc(bytes, s));
+    if (bytes) PGEOF_CUDA(cudaMemcpyAsync(d->ptr, h, bytes, cudaMemcpyHostToDevice, s));
+    return PGEOF_OK;
+}
+static int d2h(void* h, const DeviceBuffer& d, size_t bytes, cudaStream_t s)
+{
+    if (bytes) PGEOF_CUDA(cudaMemcpyAsync(h, d.ptr, bytes, cudaMemcpyDeviceToHost, s));
+    return PGEOF_OK;
+}
+
+static int check_scales(const uint32_t* k_scales, size_t n)
+{
+    uint32_t prev = 1;                                   // pgeof.hpp:123-132
+    for (size_t i = 0; i < n; ++i) { if (k_scales[i] < prev) return 0; prev = k_scales[i]; }
+    return 1;
+}
+
+__global__ void iota_scale_kernel(uint32_t* out, size_t n, uint32_t k)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)(i * k);
+}
+
+}  // namespace pgeof
+
+using namespace pgeof;
+
+#define PGEOF_REQUIRE(cond, ...)                                  \
+    do {                                                          \
+        if (!(cond)) { set_error(__VA_ARGS__); return PGEOF_EINVAL; } \
+    } while (0)
+
+extern "C" {
+
+int pgeof_abi_version(void) { return 1; }
+const char* pgeof_last_error(void) { return g_error; }
+
+int pgeof_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+int pgeof_set_device(int device)
+{
+    PGEOF_CUDA(cudaSetDevice(device));
+    return PGEOF_OK;
+}
+
+int pgeof_get_device(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return dev;
+}
+
+uint64_t pgeof_launch_count(void) { return g_launches; }
+void pgeof_reset_launch_count(void) { g_launches = 0; }
+
+int pgeof_trim(void)
+{
+    {
+        std::lock_guard<std::mutex> lock(pinned_pool().m);
+        pinned_pool().trim_locked();
+    }
+    int dev = 0;
+    if (ensure_device(&dev) != PGEOF_OK) return PGEOF_OK;
+    cudaMemPool_t pool;
+    PGEOF_CUDA(cudaDeviceSynchronize());
+    PGEOF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    PGEOF_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return PGEOF_OK;
+}
+
+void* pgeof_host_alloc(size_t bytes) { return pinned_pool().get(bytes); }
+void pgeof_host_free(void* p) { if (p) pinned_pool().put(p); }
+
+// ------------------------------- search ------------------------------------
+int pgeof_knn_search_dev(const float* data, size_t n_data, const float* query, size_t n_query, uint32_t knn,
+                         uint32_t* indices, float* sqr_dist, void* stream)
+{
+    PGEOF_REQUIRE(knn <= n_data, "knn size is greater than the data point cloud size");   // nn_search.hpp:37
+    if (n_query == 0 || knn == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(data && query && indices && sqr_dist, "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(data));
+    return search_run(SEARCH_KNN, data, n_data, query, n_query, knn, 0.f, indices, sqr_dist, nullptr, (cudaStream_t)stream);
+}
+
+int pgeof_knn_search(const float* data, size_t n_data, const float* query, size_t n_query, uint32_t knn,
+                     uint32_t* indices, float* sqr_dist)
+{
+    PGEOF_REQUIRE(knn <= n_data, "knn size is greater than the data point cloud size");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n_query == 0 || knn == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(data && query && indices && sqr_dist, "null pointer argument");
+    DeviceBuffer d_data, d_query, d_idx, d_d2;
+    PGEOF_TRY(h2d(&d_data, data, n_data * 12, s));
+    const bool self = (query == data && n_query == n_data);
+    if (!self) PGEOF_TRY(h2d(&d_query, query, n_query * 12, s));
+    const size_t out_elems = n_query * (size_t)knn;
+    PGEOF_TRY(d_idx.alloc(out_elems * 4, s));
+    PGEOF_TRY(d_d2.alloc(out_elems * 4, s));
+    PGEOF_TRY(search_run(SEARCH_KNN, d_data.as<float>(), n_data, self ? d_data.as<float>() : d_query.as<float>(), n_query, knn, 0.f,
+                         d_idx.ptr, d_d2.as<float>(), nullptr, s));
+    PGEOF_TRY(d2h(indices, d_idx, out_elems * 4, s));
+    PGEOF_TRY(d2h(sqr_dist, d_d2, out_elems * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+int pgeof_radius_search_dev(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
+                            uint32_t max_knn, int32_t* indices, float* sqr_dist, void* stream)
+{
+    PGEOF_REQUIRE(max_knn <= n_data, "max knn size is greater than the data point cloud size");   // nn_search.hpp:92-95
+    if (n_query == 0 || max_knn == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(data && query && indices && sqr_dist, "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(data));
+    return search_run(SEARCH_RADIUS, data, n_data, query, n_query, max_knn, search_radius, indices, sqr_dist, nullptr, (cudaStream_t)stream);
+}
+
+int pgeof_radius_search(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
+                        uint32_t max_knn, int32_t* indices, float* sqr_dist)
+{
+    PGEOF_REQUIRE(max_knn <= n_data, "max knn size is greater than the data point cloud size");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n_query == 0 || max_knn == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(data && query && indices && sqr_dist, "null pointer argument");
+    DeviceBuffer d_data, d_query, d_idx, d_d2;
+    PGEOF_TRY(h2d(&d_data, data, n_data * 12, s));
+    const bool self = (query == data && n_query == n_data);
+    if (!self) PGEOF_TRY(h2d(&d_query, query, n_query * 12, s));
+    const size_t out_elems = n_query * (size_t)max_knn;
+    PGEOF_TRY(d_idx.alloc(out_elems * 4, s));
+    PGEOF_TRY(d_d2.alloc(out_elems * 4, s));
+    PGEOF_TRY(search_run(SEARCH_RADIUS, d_data.as<float>(), n_data, self ? d_data.as<float>() : d_query.as<float>(), n_query, max_knn,
+                         search_radius, d_idx.ptr, d_d2.as<float>(), nullptr, s));
+    PGEOF_TRY(d2h(indices, d_idx, out_elems * 4, s));
+    PGEOF_TRY(d2h(sqr_dist, d_d2, out_elems * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+int pgeof_radius_search_csr_dev(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
+                                uint32_t max_knn, uint32_t* nn_ptr, uint32_t* nn, uint64_t* nnz, void* stream)
+{
+    PGEOF_REQUIRE(max_knn <= n_data, "max knn size is greater than the data point cloud size");
+    PGEOF_REQUIRE(nn_ptr && nnz, "null pointer argument");
+    // uint32 offsets cap a CSR at 2^32-1 neighbours: shard the queries beyond that
+    PGEOF_REQUIRE((uint64_t)n_query * max_knn <= 0xffffffffull, "n_query * max_knn exceeds the uint32 CSR limit; shard the queries");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(nn_ptr));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!nn) {   // pass 1: count + scan
+        PGEOF_CUDA(cudaMemsetAsync(nn_ptr, 0, (n_query + 1) * sizeof(uint32_t), s));
+        if (n_query && max_knn)
+            PGEOF_TRY(search_run(SEARCH_RADIUS_COUNT, data, n_data, query, n_query, max_knn, search_radius, nullptr, nullptr, nn_ptr, s));
+        PGEOF_TRY(exclusive_scan_u32(nn_ptr, n_query, s));
+        uint32_t total = 0;
+        PGEOF_CUDA(cudaMemcpyAsync(&total, nn_ptr + n_query, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        PGEOF_CUDA(cudaStreamSynchronize(s));
+        *nnz = total;
+        return PGEOF_OK;
+    }
+    if (n_query == 0 || max_knn == 0) return PGEOF_OK;
+    return search_run(SEARCH_RADIUS_CSR, data, n_data, query, n_query, max_knn, search_radius, nn, nullptr, nn_ptr, s);
+}
+
+int pgeof_radius_search_csr(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
+                            uint32_t max_knn, uint32_t* nn_ptr, uint32_t* nn, uint64_t* nnz)
+{
+    PGEOF_REQUIRE(max_knn <= n_data, "max knn size is greater than the data point cloud size");
+    PGEOF_REQUIRE(nn_ptr && nnz, "null pointer argument");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    DeviceBuffer d_data, d_query, d_ptr, d_nn;
+    PGEOF_TRY(h2d(&d_data, data, n_data * 12, s));
+    const bool self = (query == data && n_query == n_data);
+    if (!self) PGEOF_TRY(h2d(&d_query, query, n_query * 12, s));
+    const float* dq = self ? d_data.as<float>() : d_query.as<float>();
+    PGEOF_TRY(d_ptr.alloc((n_query + 1) * 4, s));
+    if (!nn) {
+        PGEOF_TRY(pgeof_radius_search_csr_dev(d_data.as<float>(), n_data, dq, n_query, search_radius, max_knn, d_ptr.as<uint32_t>(), nullptr, nnz, s));
+        PGEOF_TRY(d2h(nn_ptr, d_ptr, (n_query + 1) * 4, s));
+        PGEOF_CUDA(cudaStreamSynchronize(s));
+        return PGEOF_OK;
+    }
+    PGEOF_CUDA(cudaMemcpyAsync(d_ptr.ptr, nn_ptr, (n_query + 1) * 4, cudaMemcpyHostToDevice, s));
+    const size_t total = nn_ptr[n_query];
+    PGEOF_TRY(d_nn.alloc(total * 4, s));
+    PGEOF_TRY(pgeof_radius_search_csr_dev(d_data.as<float>(), n_data, dq, n_query, search_radius, max_knn, d_ptr.as<uint32_t>(), d_nn.as<uint32_t>(), nnz, s));
+    PGEOF_TRY(d2h(nn, d_nn, total * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    *nnz = total;
+    return PGEOF_OK;
+}
+
+// ------------------------------- features ----------------------------------
+int pgeof_compute_features_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                               size_t n_rows, uint32_t k_min, int eig_order, float* out, void* stream)
+{
+    PGEOF_REQUIRE(k_min >= 1, "k_min should be > 1");                                   // pgeof.hpp:81
+    if (n_rows == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(nn_ptr));
+    return features_run(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, k_min, eig_order, out, (cudaStream_t)stream);
+}
+
+int pgeof_compute_features_multiscale_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                                          size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out,
+                                          void* stream)
+{
+    PGEOF_REQUIRE(n_scales == 0 || k_scales, "null pointer argument");
+    PGEOF_REQUIRE(check_scales(k_scales, n_scales), "k_scales should be > 1 and sorted in ascending order");   // pgeof.hpp:165-168
+    if (n_rows == 0 || n_scales == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(nn_ptr));
+    return features_multiscale_run(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, k_scales, n_scales, eig_order, out, (cudaStream_t)stream);
+}
+
+int pgeof_compute_features_optimal_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                                       size_t n_rows, uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order,
+                                       float* out, void* stream)
+{
+    PGEOF_REQUIRE(!(k_min < 1 && k_min_search < 1), "k_min and k_min_search should be > 1");   // pgeof.hpp:250 (sic)
+    PGEOF_REQUIRE(k_step >= 1, "k_step should be >= 1");                                      // reference: modulo by zero
+    if (n_rows == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(nn_ptr));
+    return features_optimal_run(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, k_min, k_step, k_min_search, eig_order, out, (cudaStream_t)stream);
+}
+
+// host flavours of the three CSR feature functions share the staging code
+struct CsrOnDevice {
+    DeviceBuffer xyz, nn, ptr, out;
+    int stage(const float* h_xyz, size_t n_xyz, const uint32_t* h_nn, size_t nnz, const uint32_t* h_ptr, size_t n_rows, size_t out_floats,
+              cudaStream_t s)
+    {
+        PGEOF_TRY(h2d(&xyz, h_xyz, n_xyz * 12, s));
+        PGEOF_TRY(h2d(&nn, h_nn, nnz * 4, s));
+        PGEOF_TRY(h2d(&ptr, h_ptr, (n_rows + 1) * 4, s));
+        PGEOF_TRY(out.alloc(out_floats * 4, s));
+        return PGEOF_OK;
+    }
+};
+
+int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+                           uint32_t k_min, int eig_order, float* out)
+{
+    PGEOF_REQUIRE(k_min >= 1, "k_min should be > 1");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n_rows == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    CsrOnDevice d;
+    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * 11, s));
+    PGEOF_TRY(features_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_min, eig_order, d.out.as<float>(), s));
+    PGEOF_TRY(d2h(out, d.out, n_rows * 11 * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+int pgeof_compute_features_multiscale(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                                      size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out)
+{
+    PGEOF_REQUIRE(n_scales == 0 || k_scales, "null pointer argument");
+    PGEOF_REQUIRE(check_scales(k_scales, n_scales), "k_scales should be > 1 and sorted in ascending order");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n_rows == 0 || n_scales == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    CsrOnDevice d;
+    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * n_scales * 11, s));
+    PGEOF_TRY(features_multiscale_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_scales, n_scales,
+                                      eig_order, d.out.as<float>(), s));
+    PGEOF_TRY(d2h(out, d.out, n_rows * n_scales * 11 * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+int pgeof_compute_features_optimal(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+                                   uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out)
+{
+    PGEOF_REQUIRE(!(k_min < 1 && k_min_search < 1), "k_min and k_min_search should be > 1");
+    PGEOF_REQUIRE(k_step >= 1, "k_step should be >= 1");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n_rows == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    CsrOnDevice d;
+    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * 12, s));
+    PGEOF_TRY(features_optimal_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_min, k_step,
+                                   k_min_search, eig_order, d.out.as<float>(), s));
+    PGEOF_TRY(d2h(out, d.out, n_rows * 12 * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+// ------------------------------- selected ----------------------------------
+int pgeof_compute_features_selected_f32_dev(const float* xyz, size_t n, float search_radius, uint32_t max_knn, const int32_t* feature_ids,
+                                            size_t n_features, int eig_order, float* out, void* stream)
+{
+    if (n == 0 || n_features == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && feature_ids && out, "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(xyz));
+    return selected_run_f32(xyz, n, search_radius, max_knn, feature_ids, n_features, eig_order, out, (cudaStream_t)stream);
+}
+
+int pgeof_compute_features_selected_f64_dev(const double* xyz, size_t n, double search_radius, uint32_t max_knn, const int32_t* feature_ids,
+                                            size_t n_features, int eig_order, double* out, void* stream)
+{
+    if (n == 0 || n_features == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && feature_ids && out, "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(xyz));
+    return selected_run_f64(xyz, n, search_radius, max_knn, feature_ids, n_features, eig_order, out, (cudaStream_t)stream);
+}
+
+int pgeof_compute_features_selected_f32(const float* xyz, size_t n, float search_radius, uint32_t max_knn, const int32_t* feature_ids,
+                                        size_t n_features, int eig_order, float* out)
+{
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n == 0 || n_features == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && feature_ids && out, "null pointer argument");
+    DeviceBuffer d_xyz, d_out;
+    PGEOF_TRY(h2d(&d_xyz, xyz, n * 12, s));
+    PGEOF_TRY(d_out.alloc(n * n_features * 4, s));
+    PGEOF_TRY(selected_run_f32(d_xyz.as<float>(), n, search_radius, max_knn, feature_ids, n_features, eig_order, d_out.as<float>(), s));
+    PGEOF_TRY(d2h(out, d_out, n * n_features * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+int pgeof_compute_features_selected_f64(const double* xyz, size_t n, double search_radius, uint32_t max_knn, const int32_t* feature_ids,
+                                        size_t n_features, int eig_order, double* out)
+{
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n == 0 || n_features == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && feature_ids && out, "null pointer argument");
+    DeviceBuffer d_xyz, d_out;
+    PGEOF_TRY(h2d(&d_xyz, xyz, n * 24, s));
+    PGEOF_TRY(d_out.alloc(n * n_features * 8, s));
+    PGEOF_TRY(selected_run_f64(d_xyz.as<double>(), n, search_radius, max_knn, feature_ids, n_features, eig_order, d_out.as<double>(), s));
+    PGEOF_TRY(d2h(out, d_out, n * n_features * 8, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+// ------------------------------- fused pipeline ----------------------------
+int pgeof_knn_features_dev(const float* xyz, size_t n, uint32_t knn, uint32_t k_min, int eig_order, uint32_t* indices, float* sqr_dist,
+                           float* features, void* stream)
+{
+    PGEOF_REQUIRE(knn <= n, "knn size is greater than the data point cloud size");
+    PGEOF_REQUIRE(k_min >= 1, "k_min should be > 1");
+    if (n == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && features, "null pointer argument");
+    PGEOF_REQUIRE((uint64_t)n * knn <= 0xffffffffull, "n * knn exceeds the uint32 CSR limit; shard the queries");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(xyz));
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceBuffer t_idx, t_d2, ptr;
+    if (!indices) { PGEOF_TRY(t_idx.alloc(n * (size_t)knn * 4, s)); indices = t_idx.as<uint32_t>(); }
+    if (!sqr_dist) { PGEOF_TRY(t_d2.alloc(n * (size_t)knn * 4, s)); sqr_dist = t_d2.as<float>(); }
+    if (knn) PGEOF_TRY(search_run(SEARCH_KNN, xyz, n, xyz, n, knn, 0.f, indices, sqr_dist, nullptr, s));
+    PGEOF_TRY(ptr.alloc((n + 1) * 4, s));
+    iota_scale_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(ptr.as<uint32_t>(), n + 1, knn);
+    PGEOF_LAUNCH_CHECK();
+    return features_run(xyz, n, indices, n * (size_t)knn, ptr.as<uint32_t>(), n, k_min, eig_order, features, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// common.cuh -- shared declarations of the pgeof B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/pgeof_b200.h"
+
+namespace pgeof {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern thread_local uint64_t g_launches;   // kernels launched by this thread (pgeof_launch_count)
+
+#define PGEOF_CUDA(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ::pgeof::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return _e == cudaErrorMemoryAllocation ? PGEOF_ENOMEM : PGEOF_ECUDA;                  \
+        }                                                                                         \
+    } while (0)
+
+#define PGEOF_TRY(expr)            \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != PGEOF_OK) return _s; \
+    } while (0)
+
+#define PGEOF_LAUNCH_CHECK()                 \
+    do {                                     \
+        ++::pgeof::g_launches;               \
+        PGEOF_CUDA(cudaGetLastError());      \
+    } while (0)
+
+// Stream-ordered device scratch from the device's default memory pool (kept cached:
+// the release threshold is raised to "never" on first use, see capi.cu).
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    cudaStream_t stream = nullptr;
+    DeviceBuffer() = default;
+    DeviceBuffer(const DeviceBuffer&) = delete;
+    DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+    ~DeviceBuffer() { release(); }
+    int alloc(size_t bytes, cudaStream_t s);
+    void release();
+    template <typename T> T* as() const { return reinterpret_cast<T*>(ptr); }
+};
+
+// ---------------------------------------------------------------------------
+// Uniform grid index (replaces the nanoflann KD-tree, nn_search.hpp:39).
+// Cells are ordered row-major (z, y, x): the cells of one x-run are contiguous in
+// `pts`, so the candidates of a query are a handful of contiguous float4 spans.
+// ---------------------------------------------------------------------------
+struct GridView {
+    float lo[3];          // bbox minimum
+    float h;              // cell edge
+    float inv_h;          // fl(1/h)
+    float slack;          // bound on |nominal cell boundary - true assignment boundary|
+    int n[3];             // cells per axis
+    uint32_t n_pts;
+    const uint32_t* cell_start;   // [n_cells + 1]
+    const float4* pts;            // [n_pts] (x, y, z, bits(original index)), sorted by cell
+};
+
+struct Grid {
+    GridView view{};
+    DeviceBuffer cell_start, pts;
+    size_t n_cells = 0;
+};
+
+// Builds the grid over `xyz` (device, (n,3) dense).  `cell_edge` <= 0 picks the edge
+// from `target_occupancy` (mean points per cell of the bounding box).
+int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, cudaStream_t stream, Grid* out);
+
+// Sorts `query` (device, (nq,3)) by the cell of `grid` it falls in (clamped) and
+// returns float4 (x, y, z, bits(original index)) records in that order.
+int grid_sort_queries(const Grid& grid, const float* query, size_t nq, cudaStream_t stream, DeviceBuffer* out);
+
+// ---------------------------------------------------------------------------
+// search / features drivers (device pointers, asynchronous on `stream`)
+// ---------------------------------------------------------------------------
+enum SearchMode { SEARCH_KNN = 0, SEARCH_RADIUS = 1, SEARCH_RADIUS_COUNT = 2, SEARCH_RADIUS_CSR = 3 };
+
+int search_run(SearchMode mode, const float* data, size_t n_data, const float* query, size_t n_query, uint32_t k,
+               float radius, void* indices, float* sqr_dist, uint32_t* nn_ptr, cudaStream_t stream);
+
+int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+                 uint32_t k_min, int eig_order, float* out, cudaStream_t stream);
+int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                            size_t n_rows, const uint32_t* k_scales_host, size_t n_scales, int eig_order, float* out,
+                            cudaStream_t stream);
+int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                         size_t n_rows, uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out,
+                         cudaStream_t stream);
+int selected_run_f32(const float* xyz, size_t n, float radius, uint32_t max_knn, const int32_t* ids_host, size_t n_ids,
+                     int eig_order, float* out, cudaStream_t stream);
+int selected_run_f64(const double* xyz, size_t n, double radius, uint32_t max_knn, const int32_t* ids_host, size_t n_ids,
+                     int eig_order, double* out, cudaStream_t stream);
+
+// exclusive scan of `n` uint32 counts in place; writes the grand total to data[n]
+int exclusive_scan_u32(uint32_t* data, size_t n, cudaStream_t stream);
+
+// device error flag helpers (EINDEX etc.)
+int device_flag_check(const int* d_flag, cudaStream_t stream, const char* what);
+
+}  // namespace pgeof

@@ -1,0 +1,266 @@
+// grid_index.cu -- uniform-grid index build: bbox reduce, cell histogram (warp-aggregated
+// atomics that also hand every point its rank inside the cell), exclusive scan, scatter.
+// Replaces the per-call nanoflann KD-tree build (nn_search.hpp:39,97; pgeof.hpp:333).
+//
+// HBM traffic per point (n points, c cells): read 12 B (bbox) + read 12 B, write 4 B rank
+// (histogram) + read 12 B + 4 B, write 16 B (scatter) = 60 B/pt, plus 12 B per cell for the
+// scan.  All passes are streaming; the scatter writes 16-B records to random cells.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+
+#include "grid.cuh"
+
+namespace pgeof {
+
+namespace {
+
+constexpr int kBBoxBlocks = 592;   // 4 x 148 SMs
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict__ xyz, size_t n, float* __restrict__ partial)
+{
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float v = __ldg(xyz + 3 * i + d);
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    __shared__ float s[kThreads / 32][6];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { for (int d = 0; d < 3; ++d) { s[w][d] = mn[d]; s[w][3 + d] = mx[d]; } }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s[0][threadIdx.x];
+        for (int i = 1; i < kThreads / 32; ++i) v = threadIdx.x < 3 ? fminf(v, s[i][threadIdx.x]) : fmaxf(v, s[i][threadIdx.x]);
+        partial[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+// Histogram with warp-aggregated atomics.  rank[i] = position of point i inside its cell.
+__global__ void __launch_bounds__(kThreads) cell_count_kernel(GridView g, const float* __restrict__ xyz, size_t n,
+                                                              uint32_t* __restrict__ counts, uint32_t* __restrict__ rank)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t cid = 0xffffffffu;
+    if (valid) cid = cell_index(g, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned peers = __match_any_sync(active, cid);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counts + cid, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    rank[i] = base + (uint32_t)__popc(peers & lanemask_lt());
+}
+
+__global__ void __launch_bounds__(kThreads) scatter_kernel(GridView g, const float* __restrict__ xyz, size_t n,
+                                                           const uint32_t* __restrict__ cell_start,
+                                                           const uint32_t* __restrict__ rank, float4* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    const uint32_t cid = cell_index(g, x, y, z);
+    const uint32_t pos = __ldg(cell_start + cid) + __ldg(rank + i);
+    out[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)i));
+}
+
+// ---------------------------------------------------------------------------
+// exclusive scan, three passes: tile sums -> scan of tile sums -> rescan + offset
+// ---------------------------------------------------------------------------
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kThreads * kScanItems;   // 4096 counts per block
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total)
+{
+    __shared__ uint32_t warp_sums[kThreads / 32];
+    __shared__ uint32_t block_total;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t ws = lane < kThreads / 32 ? warp_sums[lane] : 0;
+        uint32_t winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < kThreads / 32) warp_sums[lane] = winc - ws;
+        if (lane == kThreads / 32 - 1) block_total = winc;
+    }
+    __syncthreads();
+    const uint32_t r = warp_sums[w] + inc - v;
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_tile_sums(const uint32_t* __restrict__ data, size_t n, uint32_t* __restrict__ tile_sums)
+{
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) if (base + j < n) s += data[base + j];
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_tile_offsets(uint32_t* __restrict__ tile_sums, size_t n_tiles, uint32_t* __restrict__ grand_total)
+{
+    uint32_t carry = 0;
+    for (size_t base = 0; base < n_tiles; base += kThreads) {
+        const size_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? tile_sums[i] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < n_tiles) tile_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_apply(uint32_t* __restrict__ data, size_t n, const uint32_t* __restrict__ tile_offsets)
+{
+    const size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) { v[j] = base + j < n ? data[base + j] : 0; s += v[j]; }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(s, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+        if (base + j < n) data[base + j] = run;
+        run += v[j];
+    }
+}
+
+}  // namespace
+
+int exclusive_scan_u32(uint32_t* data, size_t n, cudaStream_t stream)
+{
+    if (n == 0) { PGEOF_CUDA(cudaMemsetAsync(data, 0, sizeof(uint32_t), stream)); return PGEOF_OK; }
+    const size_t n_tiles = (n + kScanTile - 1) / kScanTile;
+    DeviceBuffer sums;
+    PGEOF_TRY(sums.alloc(n_tiles * sizeof(uint32_t), stream));
+    scan_tile_sums<<<(unsigned)n_tiles, kThreads, 0, stream>>>(data, n, sums.as<uint32_t>());
+    PGEOF_LAUNCH_CHECK();
+    scan_tile_offsets<<<1, kThreads, 0, stream>>>(sums.as<uint32_t>(), n_tiles, data + n);
+    PGEOF_LAUNCH_CHECK();
+    scan_apply<<<(unsigned)n_tiles, kThreads, 0, stream>>>(data, n, sums.as<uint32_t>());
+    PGEOF_LAUNCH_CHECK();
+    return PGEOF_OK;
+}
+
+static size_t max_cells_for(size_t n)
+{
+    // the dense cell table costs 12 B of scan traffic per cell; keep it comparable to the point data
+    size_t cap = std::max<size_t>(8 * n, (size_t)1 << 20);
+    if (const char* e = std::getenv("PGEOF_MAX_CELLS")) cap = (size_t)std::strtoull(e, nullptr, 10);
+    return std::min<size_t>(cap, (size_t)1 << 28);
+}
+
+int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, cudaStream_t stream, Grid* out)
+{
+    if (n == 0 || n > 0xfffffff0ull) { set_error("grid_build: n=%zu out of range", n); return PGEOF_EINVAL; }
+    // 1. bounding box
+    DeviceBuffer partial;
+    PGEOF_TRY(partial.alloc(kBBoxBlocks * 6 * sizeof(float), stream));
+    bbox_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(xyz, n, partial.as<float>());
+    PGEOF_LAUNCH_CHECK();
+    float hp[kBBoxBlocks * 6];
+    PGEOF_CUDA(cudaMemcpyAsync(hp, partial.ptr, sizeof(hp), cudaMemcpyDeviceToHost, stream));
+    PGEOF_CUDA(cudaStreamSynchronize(stream));
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int b = 0; b < kBBoxBlocks; ++b)
+        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], hp[b * 6 + d]); hi[d] = std::max(hi[d], hp[b * 6 + 3 + d]); }
+    double ext[3], maxabs = 0;
+    for (int d = 0; d < 3; ++d) {
+        if (!(lo[d] <= hi[d]) || !std::isfinite(lo[d]) || !std::isfinite(hi[d])) {
+            set_error("point cloud holds non-finite coordinates"); return PGEOF_EINVAL;
+        }
+        ext[d] = (double)hi[d] - (double)lo[d];
+        maxabs = std::max(maxabs, std::max(std::fabs((double)lo[d]), std::fabs((double)hi[d])));
+    }
+    // 2. cell edge
+    double h = cell_edge;
+    if (!(h > 0)) {
+        double vol = 1; int dims = 0;
+        for (int d = 0; d < 3; ++d) if (ext[d] > 0) { vol *= ext[d]; ++dims; }
+        h = dims ? std::pow(vol * std::max(1.0f, target_occupancy) / (double)n, 1.0 / dims) : 1.0;
+    }
+    // float32 cannot resolve cells much finer than an ulp of the coordinates
+    h = std::max(h, std::max(maxabs * 1e-5, 1e-30));
+    const size_t cap = max_cells_for(n);
+    int nc[3];
+    for (;;) {
+        double cells = 1;
+        for (int d = 0; d < 3; ++d) { const double c = std::floor(ext[d] / h) + 1; nc[d] = (int)std::min(c, 2e9); cells *= c; }
+        if (cells <= (double)cap) break;
+        h *= 1.26;
+    }
+    GridView& g = out->view;
+    for (int d = 0; d < 3; ++d) { g.lo[d] = lo[d]; g.n[d] = nc[d]; }
+    g.h = (float)h;
+    g.inv_h = 1.0f / g.h;
+    g.slack = (float)((2.0 * maxabs + h) * 9.5367431640625e-7);   // 2^-20
+    g.n_pts = (uint32_t)n;
+    out->n_cells = (size_t)nc[0] * nc[1] * nc[2];
+    // 3. histogram -> scan -> scatter
+    PGEOF_TRY(out->cell_start.alloc((out->n_cells + 1) * sizeof(uint32_t), stream));
+    PGEOF_TRY(out->pts.alloc(n * sizeof(float4), stream));
+    DeviceBuffer rank;
+    PGEOF_TRY(rank.alloc(n * sizeof(uint32_t), stream));
+    uint32_t* cs = out->cell_start.as<uint32_t>();
+    PGEOF_CUDA(cudaMemsetAsync(cs, 0, (out->n_cells + 1) * sizeof(uint32_t), stream));
+    const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
+    cell_count_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>());
+    PGEOF_LAUNCH_CHECK();
+    PGEOF_TRY(exclusive_scan_u32(cs, out->n_cells, stream));
+    scatter_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), out->pts.as<float4>());
+    PGEOF_LAUNCH_CHECK();
+    g.cell_start = cs;
+    g.pts = out->pts.as<float4>();
+    return PGEOF_OK;
+}
+
+int grid_sort_queries(const Grid& grid, const float* query, size_t nq, cudaStream_t stream, DeviceBuffer* out)
+{
+    PGEOF_TRY(out->alloc(std::max<size_t>(nq, 1) * sizeof(float4), stream));
+    if (nq == 0) return PGEOF_OK;
+    DeviceBuffer counts, rank;
+    PGEOF_TRY(counts.alloc((grid.n_cells + 1) * sizeof(uint32_t), stream));
+    PGEOF_TRY(rank.alloc(nq * sizeof(uint32_t), stream));
+    PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, (grid.n_cells + 1) * sizeof(uint32_t), stream));
+    const unsigned blocks = (unsigned)((nq + kThreads - 1) / kThreads);
+    cell_count_kernel<<<blocks, kThreads, 0, stream>>>(grid.view, query, nq, counts.as<uint32_t>(), rank.as<uint32_t>());
+    PGEOF_LAUNCH_CHECK();
+    PGEOF_TRY(exclusive_scan_u32(counts.as<uint32_t>(), grid.n_cells, stream));
+    scatter_kernel<<<blocks, kThreads, 0, stream>>>(grid.view, query, nq, counts.as<uint32_t>(), rank.as<uint32_t>(), out->as<float4>());
+    PGEOF_LAUNCH_CHECK();
+    return PGEOF_OK;
+}
+
+}  // namespace pgeof
