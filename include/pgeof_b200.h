@@ -71,6 +71,15 @@ PGEOF_API void pgeof_reset_launch_count(void);
 /* release cached device workspaces and pinned staging of the current device */
 PGEOF_API int pgeof_trim(void);
 
+/* Per-kernel device timing (CUDA events on the launching stream) for roofline reports.
+ * Off by default; when on, every hot kernel launch is bracketed by two events.
+ * pgeof_profile_read sums the launches of kernel `name` ("knn_search", "radius_search",
+ * "features", "multiscale", "optimal", "selected", "grid_build") since the last reset;
+ * it synchronises those events.  Returns PGEOF_EINVAL for an unknown name. */
+PGEOF_API void pgeof_profile_enable(int on);
+PGEOF_API void pgeof_profile_reset(void);
+PGEOF_API int pgeof_profile_read(const char* name, double* total_ms, uint64_t* launches);
+
 /* Pinned host memory from the library's caching pool.  The binding backs numpy
  * result arrays with it so the D2H copy of a result is a single DMA. */
 PGEOF_API void* pgeof_host_alloc(size_t bytes);

@@ -290,8 +290,11 @@ PCA<T> pca_from_cloud(const T* cloud, size_t k, int eig_order)
     T w[3], V[3][3];
     eig3_sym(cov, w, V);
     PCA<T> p;
+    int perm[3] = {0, 1, 2};
+    if (eig_order != 0)   // documented: decreasing, stable (ties keep the solver's column order)
+        std::stable_sort(perm, perm + 3, [&](int a, int b) { return w[a] > w[b]; });
     for (int s = 0; s < 3; ++s) {
-        const int c = eig_order == 0 ? s : 2 - s;
+        const int c = perm[s];
         p.val[s] = std::max(w[c], T(0));
         T* dst = s == 0 ? p.v0 : (s == 1 ? p.v1 : p.v2);
         for (int r = 0; r < 3; ++r) dst[r] = V[r][c];

@@ -60,8 +60,8 @@ def pca_from_pointcloud(cloud, eig_order="literal"):
     cov = centered.T @ centered / float(k)                # :76 (population cov)
     w, v = np.linalg.eigh(cov)                            # :79 ascending, like Eigen
     if eig_order == "documented":
-        w = w[::-1]
-        v = v[:, ::-1]
+        o = np.argsort(-w, kind="stable")                 # decreasing; ties keep Eigen's column order
+        w, v = w[o], v[:, o]
     elif eig_order != "literal":
         raise ValueError("eig_order must be 'literal' or 'documented'")
     val = np.maximum(w, 0.0)                              # :85 clamp

@@ -37,6 +37,9 @@ from .pgeof_ext import (  # noqa: E402,F401
     get_eig_order,
     knn_features,
     launch_count,
+    profile_enable,
+    profile_read,
+    profile_reset,
     radius_search_csr,
     reset_launch_count,
     set_eig_order,

@@ -444,5 +444,12 @@ PYBIND11_MODULE(pgeof_ext, m)
     m.def("launch_count", [] { return pgeof_launch_count(); });
     m.def("reset_launch_count", [] { pgeof_reset_launch_count(); });
     m.def("trim", [] { check(pgeof_trim()); });
+    m.def("profile_enable", [](bool on) { pgeof_profile_enable(on ? 1 : 0); }, "on"_a);
+    m.def("profile_reset", [] { pgeof_profile_reset(); });
+    m.def("profile_read", [](const std::string& name) {
+        double ms = 0; uint64_t n = 0;
+        check(pgeof_profile_read(name.c_str(), &ms, &n));
+        return py::make_tuple(ms, n);
+    }, "name"_a, "(total device ms, launches) of one hot kernel since the last profile_reset().");
     m.attr("abi_version") = pgeof_abi_version();
 }

@@ -25,6 +25,34 @@ void set_error(const char* fmt, ...)
 }
 
 // ---------------------------------------------------------------------------
+// optional per-kernel event timing
+// ---------------------------------------------------------------------------
+static const char* const kTimerNames[] = {"knn_search", "radius_search", "features", "multiscale", "optimal", "selected", "grid_build"};
+constexpr int kNumTimers = sizeof(kTimerNames) / sizeof(kTimerNames[0]);
+static bool g_profile = false;
+static std::mutex g_profile_mutex;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profile_events[kNumTimers];
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t s) : stream(s)
+{
+    if (!g_profile) return;
+    for (int i = 0; i < kNumTimers; ++i) if (std::strcmp(name, kTimerNames[i]) == 0) slot = i;
+    if (slot < 0) return;
+    if (cudaEventCreate(&start) != cudaSuccess) { slot = -1; cudaGetLastError(); return; }
+    cudaEventRecord(start, stream);
+}
+
+KernelTimer::~KernelTimer()
+{
+    if (slot < 0) return;
+    cudaEvent_t stop;
+    if (cudaEventCreate(&stop) != cudaSuccess) { cudaGetLastError(); cudaEventDestroy(start); return; }
+    cudaEventRecord(stop, stream);
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    g_profile_events[slot].emplace_back(start, stop);
+}
+
+// ---------------------------------------------------------------------------
 // device scratch: cudaMallocAsync on the device's default pool, never trimmed
 // ---------------------------------------------------------------------------
 static std::mutex g_pool_mutex;
@@ -236,6 +264,35 @@ int pgeof_trim(void)
     PGEOF_CUDA(cudaDeviceSynchronize());
     PGEOF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
     PGEOF_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return PGEOF_OK;
+}
+
+void pgeof_profile_enable(int on) { g_profile = on != 0; }
+
+void pgeof_profile_reset(void)
+{
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    for (auto& v : g_profile_events) {
+        for (auto& p : v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+        v.clear();
+    }
+}
+
+int pgeof_profile_read(const char* name, double* total_ms, uint64_t* launches)
+{
+    int slot = -1;
+    for (int i = 0; i < kNumTimers; ++i) if (name && std::strcmp(name, kTimerNames[i]) == 0) slot = i;
+    if (slot < 0) { set_error("unknown kernel timer '%s'", name ? name : "(null)"); return PGEOF_EINVAL; }
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    double sum = 0;
+    for (auto& p : g_profile_events[slot]) {
+        PGEOF_CUDA(cudaEventSynchronize(p.second));
+        float ms = 0;
+        PGEOF_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = g_profile_events[slot].size();
     return PGEOF_OK;
 }
 

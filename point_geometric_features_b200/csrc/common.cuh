@@ -39,6 +39,15 @@ extern thread_local uint64_t g_launches;   // kernels launched by this thread (p
         PGEOF_CUDA(cudaGetLastError());      \
     } while (0)
 
+// Brackets a kernel launch with CUDA events when profiling is on (pgeof_profile_enable).
+struct KernelTimer {
+    int slot = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t start = nullptr;
+    KernelTimer(const char* name, cudaStream_t s);
+    ~KernelTimer();
+};
+
 // Stream-ordered device scratch from the device's default memory pool (kept cached:
 // the release threshold is raised to "never" on first use, see capi.cu).
 struct DeviceBuffer {

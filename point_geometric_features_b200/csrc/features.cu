@@ -310,11 +310,14 @@ int make_args(FeatArgs* a, const float* xyz, size_t n_xyz, const uint32_t* nn, s
 }
 
 template <typename K>
-int launch_tiles(K kern, const FeatArgs& a, size_t smem, cudaStream_t stream)
+int launch_tiles(K kern, const char* name, const FeatArgs& a, size_t smem, cudaStream_t stream)
 {
     if (smem > 48 * 1024) PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_rows + kRows - 1) / kRows;
-    kern<<<blocks, kRows, smem, stream>>>(a);
+    {
+        KernelTimer timer(name, stream);
+        kern<<<blocks, kRows, smem, stream>>>(a);
+    }
     PGEOF_LAUNCH_CHECK();
     return PGEOF_OK;
 }
@@ -343,7 +346,7 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
     a.k_min = k_min;
     const size_t fixed = 128 + kRows * 11 * sizeof(float);
     a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
-    PGEOF_TRY(launch_tiles(features_kernel, a, fixed + (size_t)a.nn_cap * 4, stream));
+    PGEOF_TRY(launch_tiles(features_kernel, "features", a, fixed + (size_t)a.nn_cap * 4, stream));
     return device_flag_check(err.as<int>(), stream, "compute_features");
 }
 
@@ -366,7 +369,7 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
         a.scale_base = (uint32_t)base;
         a.n_scales_pass = (uint32_t)std::min<size_t>(kMaxScalesPerPass, n_scales - base);
         for (uint32_t s = 0; s < a.n_scales_pass; ++s) a.scales[s] = k_scales_host[base + s];
-        PGEOF_TRY(launch_tiles(multiscale_kernel, a, fixed + (size_t)a.nn_cap * 4, stream));
+        PGEOF_TRY(launch_tiles(multiscale_kernel, "multiscale", a, fixed + (size_t)a.nn_cap * 4, stream));
     }
     return device_flag_check(err.as<int>(), stream, "compute_features_multiscale");
 }
@@ -384,7 +387,7 @@ int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, siz
     a.k_min = k_min; a.k_step = k_step; a.k_min_search = k_min_search;
     const size_t fixed = 128 + kRows * 12 * sizeof(float);
     a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
-    PGEOF_TRY(launch_tiles(optimal_kernel, a, fixed + (size_t)a.nn_cap * 4, stream));
+    PGEOF_TRY(launch_tiles(optimal_kernel, "optimal", a, fixed + (size_t)a.nn_cap * 4, stream));
     return device_flag_check(err.as<int>(), stream, "compute_features_optimal");
 }
 

@@ -185,6 +185,7 @@ static size_t max_cells_for(size_t n)
 int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, cudaStream_t stream, Grid* out)
 {
     if (n == 0 || n > 0xfffffff0ull) { set_error("grid_build: n=%zu out of range", n); return PGEOF_EINVAL; }
+    KernelTimer timer("grid_build", stream);
     // 1. bounding box
     DeviceBuffer partial;
     PGEOF_TRY(partial.alloc(kBBoxBlocks * 6 * sizeof(float), stream));

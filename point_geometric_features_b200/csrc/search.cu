@@ -199,7 +199,10 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     auto kern = search_kernel<NSORT, MODE>;
     if (smem > 48 * 1024) PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + kWarps - 1) / kWarps;
-    kern<<<blocks, kWarps * 32, smem, stream>>>(g, a);
+    {
+        KernelTimer timer(MODE == SEARCH_KNN ? "knn_search" : "radius_search", stream);
+        kern<<<blocks, kWarps * 32, smem, stream>>>(g, a);
+    }
     PGEOF_LAUNCH_CHECK();
     return PGEOF_OK;
 }

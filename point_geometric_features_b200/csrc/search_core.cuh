@@ -173,7 +173,7 @@ __device__ __forceinline__ u64 select_threshold(const u64 (&key)[MC], uint32_t c
     u64 lo = 0;
     float cur_cnt = (float)c, cur_d2 = key_d2(hi);
     const float target = 0.5f * (float)(need + cap_hi);
-    for (int it = 0;; ++it) {
+    for (int it = 0; it < 96; ++it) {   // 64-bit bisection needs <= 64 steps; the cap only guards against a hang
         u64 mid = lo + (hi - lo) / 2;
         if (it < 3) {
             const float gd2 = cur_d2 * exp2f(0.6666667f * log2f(target / cur_cnt));
@@ -187,6 +187,7 @@ __device__ __forceinline__ u64 select_threshold(const u64 (&key)[MC], uint32_t c
         cur_cnt = fmaxf((float)n, 0.5f);
         cur_d2 = key_d2(mid);
     }
+    return hi;
 }
 
 // Bitonic sort of 32*M keys held as v[m] at element index m*32 + lane, ascending.

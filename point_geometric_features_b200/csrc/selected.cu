@@ -239,7 +239,10 @@ int selected_run(const T* xyz, const float* xyz_f32, size_t n, T radius, uint32_
     PGEOF_CUDA(cudaMemcpyAsync(ids.ptr, ids_host, n_ids * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
     SelArgs<T> a{xyz, (uint32_t)n, radius, max_knn, ids.as<int32_t>(), (uint32_t)n_ids, eig_order, out};
     const unsigned blocks = (unsigned)((n + kWarps - 1) / kWarps);
-    selected_kernel<T><<<blocks, kWarps * 32, 0, stream>>>(grid.view, a);
+    {
+        KernelTimer timer("selected", stream);
+        selected_kernel<T><<<blocks, kWarps * 32, 0, stream>>>(grid.view, a);
+    }
     PGEOF_LAUNCH_CHECK();
     // ids_host may be a temporary of the caller: the pageable H2D copy above is staged
     // synchronously by the runtime, so no extra synchronisation is needed here.

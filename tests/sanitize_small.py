@@ -1,0 +1,30 @@
+"""Small invocation of every entry point, meant to run under compute-sanitizer on the GPU box:
+    compute-sanitizer --tool memcheck python tests/sanitize_small.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pgeof  # noqa: E402
+import point_geometric_features_b200 as b200  # noqa: E402
+from point_geometric_features_b200 import synth  # noqa: E402
+
+xyz = synth.lidar_like_cloud(6000, seed=0)
+for k in (5, 40, 100, 300):
+    idx, d2 = pgeof.knn_search(xyz, xyz, k)
+q = np.concatenate([xyz[:500], np.random.default_rng(0).uniform(-50, 200, (200, 3)).astype(np.float32)])
+pgeof.knn_search(xyz, q, 20)
+ridx, _ = pgeof.radius_search(xyz, xyz, 0.5, 32)
+nn, nn_ptr = synth.radius_csr(ridx)
+pgeof.compute_features(xyz, nn, nn_ptr, 3)
+pgeof.compute_features_multiscale(xyz, nn, nn_ptr, [2, 4, 8, 16, 32])
+pgeof.compute_features_optimal(xyz, nn, nn_ptr, 1, 2, 4)
+nn2, ptr2 = b200.radius_search_csr(xyz, xyz, 0.5, 32)
+assert (nn2 == nn).all() and (ptr2 == nn_ptr).all()
+pgeof.compute_features_selected(xyz, 0.4, 10, [pgeof.EFeatureID.Verticality, pgeof.EFeatureID.Eigentropy])
+pgeof.compute_features_selected(xyz.astype(np.float64), 0.4, 10, [pgeof.EFeatureID.Verticality, pgeof.EFeatureID.Eigentropy])
+nn3, ptr3 = synth.knn_csr(idx)
+pgeof.compute_features(xyz, nn3, ptr3)
+print("sanitize_small ok")

@@ -1,0 +1,431 @@
+"""GPU parity tests: the CUDA path, called through the drop-in Python surface and the C ABI, against
+the CPU oracle on the same seeded inputs.  Bars (BASELINE.json:north_star): neighbour indices and
+squared distances bit-exact with (d2, index) tie-breaking; optimal-k exact; the 11 features within
+1e-4 absolute / 1e-3 relative (tests/helpers.py states the conditioning-aware exemptions)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+from scipy.spatial import KDTree
+
+import pgeof
+import point_geometric_features_b200 as b200
+from oracle import cpu, ref_numpy as rn
+from point_geometric_features_b200 import synth
+from tests.helpers import compare_features, knn_csr, radius_csr, row_eigvals, row_eigvals_dense
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "readme_600.npz")
+ORDERS = ("literal", "documented")
+
+
+@pytest.fixture(autouse=True)
+def _literal_order():
+    b200.set_eig_order("literal")
+    yield
+    b200.set_eig_order("env")
+
+
+def _assert_search_equal(got, ref):
+    np.testing.assert_array_equal(got[0], ref[0])
+    np.testing.assert_array_equal(got[1].view(np.uint32), ref[1].view(np.uint32))   # bit-exact float32
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's own three tests (tests/test_pgeof.py:8-46), seeded, against the new module
+# --------------------------------------------------------------------------------------------
+def test_upstream_knn():
+    xyz = np.random.default_rng(0).uniform(0.0, 200.0, size=(1000, 3)).astype(np.float32)
+    _, k_legacy = KDTree(xyz).query(xyz, k=10, workers=-1)
+    k_new, _ = pgeof.knn_search(xyz, xyz, 10)
+    assert k_new.dtype == np.uint32 and k_new.shape == (1000, 10)
+    np.testing.assert_equal(k_legacy, k_new)
+
+
+def test_upstream_radius_search():
+    xyz = np.random.default_rng(0).random(size=(1000, 3), dtype=np.float32)
+    _, k_legacy = KDTree(xyz).query(xyz, k=10, distance_upper_bound=0.2, workers=-1)
+    k_legacy[k_legacy == xyz.shape[0]] = -1
+    k_new, d2 = pgeof.radius_search(xyz, xyz, 0.2, 10)
+    assert k_new.dtype == np.int32 and d2.dtype == np.float32
+    np.testing.assert_equal(k_legacy, k_new)
+
+
+def test_upstream_multiscale():
+    xyz = np.random.default_rng(0).uniform(0.0, 200.0, size=(10000, 3)).astype(np.float32)
+    kneigh = KDTree(xyz).query(xyz, k=50, workers=-1)
+    nn_ptr = (np.arange(10000 + 1) * 50).astype("uint32")
+    nn = np.ascontiguousarray(kneigh[1].flatten().astype("uint32"))
+    multi = pgeof.compute_features_multiscale(xyz, nn, nn_ptr, np.flip(np.array([50, 20])), False)
+    simple = pgeof.compute_features(xyz, nn, nn_ptr, 50, False)
+    multi_simple = pgeof.compute_features_multiscale(xyz, nn, nn_ptr, [20], False)
+    assert multi.shape == (10000, 2, 11) and simple.shape == (10000, 11)
+    np.testing.assert_allclose(multi[:, 0], multi_simple[:, 0], 1e-1, 1e-5)
+    np.testing.assert_allclose(multi[:, 1], simple, 1e-1, 1e-5)
+
+
+def test_golden_fixture():
+    g = np.load(GOLD)
+    xyz = g["xyz"]
+    _assert_search_equal(pgeof.knn_search(xyz, xyz, 20), (g["knn_idx"], g["knn_d2"]))
+    _assert_search_equal(pgeof.radius_search(xyz, xyz, 0.2, 10), (g["radius_idx"], g["radius_d2"]))
+    nn, nn_ptr = knn_csr(g["knn_idx"])
+    ev = row_eigvals_dense(xyz, g["knn_idx"])
+    for order in ORDERS:
+        b200.set_eig_order(order)
+        compare_features(pgeof.compute_features(xyz, nn, nn_ptr), g["features_" + order], ev, order)
+        ms = pgeof.compute_features_multiscale(xyz, nn, nn_ptr, [5, 10, 20])
+        for s, ks in enumerate((5, 10, 20)):
+            compare_features(ms[:, s], g["multiscale_" + order][:, s], row_eigvals_dense(xyz, g["knn_idx"][:, :ks]), order, "scale %d" % ks)
+        opt = pgeof.compute_features_optimal(xyz, nn, nn_ptr, 1, 1, 5)
+        sure = g["optimal_margin_" + order] > 1e-9
+        np.testing.assert_array_equal(opt[sure, 11], g["optimal_" + order][sure, 11])
+
+
+# --------------------------------------------------------------------------------------------
+# neighbour search: bit-exact against the (d2, index) oracle
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k", [1, 2, 10, 20, 32, 33, 50, 64, 65, 100, 128, 129, 200, 256, 300, 512])
+def test_knn_uniform_bitexact(k):
+    xyz = synth.uniform_cloud(20000, seed=k)
+    _assert_search_equal(pgeof.knn_search(xyz, xyz, k), cpu.knn_search(xyz, xyz, k))
+
+
+def test_knn_c2_subsample_bitexact():
+    """BASELINE config 2 (1M uniform pts, k=50): 1M on the GPU, oracle on the full cloud for 20k sampled queries."""
+    xyz = synth.uniform_cloud(1_000_000, seed=0)
+    idx, d2 = pgeof.knn_search(xyz, xyz, 50)
+    rows = np.random.default_rng(1).choice(len(xyz), 20000, replace=False)
+    ref = cpu.knn_search(xyz, xyz[rows], 50)
+    _assert_search_equal((idx[rows], d2[rows]), ref)
+    assert (idx[:, 0] == np.arange(len(xyz))).all() and (d2[:, 0] == 0).all()      # self first: d2 = 0, lowest index
+    assert (np.diff(d2, axis=1) >= 0).all()                                       # rows ascending
+
+
+def test_knn_query_differs_from_data_and_leaves_bbox():
+    rng = np.random.default_rng(2)
+    data = synth.uniform_cloud(30000, seed=3, extent=50.0)
+    query = np.concatenate([rng.uniform(0, 50, (2000, 3)), rng.uniform(-40, 90, (1500, 3)), rng.uniform(-1e4, 1e4, (50, 3)),
+                            data[:100]]).astype(np.float32)
+    for k in (1, 16, 50):
+        _assert_search_equal(pgeof.knn_search(data, query, k), cpu.knn_search(data, query, k))
+
+
+def test_knn_ties_duplicates_lattice_and_degenerate_shapes():
+    rng = np.random.default_rng(4)
+    g = np.stack(np.meshgrid(*[np.arange(12)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    lattice = np.concatenate([g, g[rng.integers(0, len(g), 500)]])[rng.permutation(len(g) + 500)]     # exact ties + duplicates
+    heavy_dup = np.concatenate([np.tile(np.float32([[1, 2, 3]]), (700, 1)), rng.uniform(0, 5, (300, 3)).astype(np.float32)])
+    plane = np.c_[rng.uniform(0, 10, (5000, 2)), np.zeros(5000)].astype(np.float32)                   # zero z extent
+    line = np.c_[rng.uniform(0, 10, 3000), np.full(3000, 2.0), np.full(3000, -1.0)].astype(np.float32)
+    single = np.float32([[3, 3, 3]])
+    for name, xyz, ks in (("lattice", lattice, (1, 7, 27, 50)), ("heavy_dup", heavy_dup, (5, 50, 300)), ("plane", plane, (8, 50)),
+                          ("line", line, (8, 50)), ("single", single, (1,)), ("tiny", lattice[:5], (5,))):
+        for k in ks:
+            got, ref = pgeof.knn_search(xyz, xyz, k), cpu.knn_search(xyz, xyz, k, brute=len(xyz) < 4000)
+            np.testing.assert_array_equal(got[0], ref[0], err_msg="%s k=%d" % (name, k))
+            np.testing.assert_array_equal(got[1], ref[1], err_msg="%s k=%d" % (name, k))
+
+
+def test_knn_lidar_like_bitexact():
+    xyz = synth.lidar_like_cloud(300000, seed=0)
+    idx, d2 = pgeof.knn_search(xyz, xyz, 30)
+    rows = np.random.default_rng(5).choice(len(xyz), 20000, replace=False)
+    _assert_search_equal((idx[rows], d2[rows]), cpu.knn_search(xyz, xyz[rows], 30))
+
+
+@pytest.mark.parametrize("r,max_knn", [(0.2, 10), (0.05, 10), (0.2, 1), (0.35, 64), (0.3, 100), (0.0, 4), (2.0, 32)])
+def test_radius_unit_cube_bitexact(r, max_knn):
+    xyz = np.random.default_rng(6).random((3000, 3), dtype=np.float32)
+    _assert_search_equal(pgeof.radius_search(xyz, xyz, r, max_knn), cpu.radius_search(xyz, xyz, r, max_knn))
+
+
+def test_radius_lidar_like_c3_subsample():
+    """BASELINE config 3 shape (LiDAR-like, r=0.2, max_k=64) at 400k points."""
+    xyz = synth.lidar_like_cloud(400000, seed=1)
+    idx, d2 = pgeof.radius_search(xyz, xyz, 0.2, 64)
+    rows = np.random.default_rng(7).choice(len(xyz), 20000, replace=False)
+    _assert_search_equal((idx[rows], d2[rows]), cpu.radius_search(xyz, xyz[rows], 0.2, 64))
+    # CSR emitted directly == README glue on the padded result (README.md:157-163)
+    nn, nn_ptr = b200.radius_search_csr(xyz, xyz, 0.2, 64)
+    nn_ref, ptr_ref = radius_csr(idx)
+    np.testing.assert_array_equal(nn_ptr, ptr_ref)
+    np.testing.assert_array_equal(nn, nn_ref)
+
+
+def test_radius_dense_ball_overflows_candidate_buffer():
+    """> 512 points inside the ball: the threshold is bisected by rescans, result still exact."""
+    rng = np.random.default_rng(8)
+    xyz = np.concatenate([rng.normal(0, 0.05, (3000, 3)), rng.uniform(-2, 2, (2000, 3))]).astype(np.float32)
+    q = xyz[:400]
+    for max_knn in (16, 64, 200):
+        _assert_search_equal(pgeof.radius_search(xyz, q, 0.5, max_knn), cpu.radius_search(xyz, q, 0.5, max_knn))
+    _assert_search_equal(pgeof.knn_search(xyz, q, 40), cpu.knn_search(xyz, q, 40))
+
+
+def test_search_edge_cases():
+    xyz = synth.uniform_cloud(100, seed=9)
+    idx, d2 = pgeof.knn_search(xyz, xyz[:0], 5)
+    assert idx.shape == (0, 5) and d2.shape == (0, 5)
+    idx, d2 = pgeof.knn_search(xyz, xyz, 0)
+    assert idx.shape == (100, 0)
+    idx, d2 = pgeof.radius_search(xyz, xyz, 1e9, 100)                               # everything, max_knn == n
+    _assert_search_equal((idx, d2), cpu.radius_search(xyz, xyz, 1e9, 100))
+    _assert_search_equal(pgeof.knn_search(xyz, xyz, 100), cpu.knn_search(xyz, xyz, 100))   # knn == n
+    with pytest.raises(ValueError):
+        pgeof.knn_search(xyz, xyz, 101)
+    strided = np.zeros((100, 4), np.float32)[:, :3]                                  # row stride 16 B, unit inner stride
+    strided[:] = xyz
+    _assert_search_equal(pgeof.knn_search(strided, strided, 7), cpu.knn_search(xyz, xyz, 7))
+
+
+# --------------------------------------------------------------------------------------------
+# features
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("order", ORDERS)
+def test_features_c1_readme_example(order):
+    """BASELINE config 1: 10k uniform [0,1)^3 float32 points, knn_search k=20 -> CSR -> compute_features."""
+    b200.set_eig_order(order)
+    xyz = np.random.default_rng(10).random((10000, 3)).astype("float32")
+    knn, _ = pgeof.knn_search(xyz, xyz, 20)
+    nn_ptr = (np.arange(10000 + 1) * 20).astype("uint32")
+    nn = knn.flatten().astype("uint32")
+    f = pgeof.compute_features(xyz, nn, nn_ptr)
+    assert f.dtype == np.float32 and f.shape == (10000, 11)
+    compare_features(f, cpu.compute_features(xyz, nn, nn_ptr, 1, order), row_eigvals_dense(xyz, knn), order)
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_features_c2_subsample(order):
+    b200.set_eig_order(order)
+    xyz = synth.uniform_cloud(200000, seed=11)
+    idx, _ = pgeof.knn_search(xyz, xyz, 50)
+    nn, nn_ptr = knn_csr(idx)
+    f = pgeof.compute_features(xyz, nn, nn_ptr)
+    stats = compare_features(f, cpu.compute_features(xyz, nn, nn_ptr, 1, order), row_eigvals_dense(xyz, idx), order)
+    assert stats["ill_conditioned_rows"] < 0.001 * len(xyz) and stats["degenerate_rows"] == 0
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_features_ragged_lidar_rows_and_kmin(order):
+    b200.set_eig_order(order)
+    xyz = synth.lidar_like_cloud(120000, seed=2)
+    idx, _ = pgeof.radius_search(xyz, xyz, 0.3, 48)
+    nn, nn_ptr = radius_csr(idx)
+    ev = row_eigvals(xyz, nn, nn_ptr)
+    for k_min in (1, 5, 30):
+        f = pgeof.compute_features(xyz, nn, nn_ptr, k_min)
+        ref = cpu.compute_features(xyz, nn, nn_ptr, k_min, order)
+        short = np.diff(nn_ptr.astype(np.int64)) < k_min
+        assert (f[short] == 0).all()                                                # calloc semantics, pgeof.hpp:88,103
+        compare_features(f, ref, ev, order, "k_min=%d" % k_min)
+
+
+def test_features_known_answers_and_errors():
+    xyz = np.array([[1, 2, 3], [1, 2, 3], [1, 2, 3], [4, 4, 4]], np.float32)
+    nn = np.array([0, 0, 1, 2, 3], np.uint32)
+    nn_ptr = np.array([0, 1, 4, 4, 5], np.uint32)
+    f = pgeof.compute_features(xyz, nn, nn_ptr)
+    expect = np.float32([0, 0, 0, 0, 0, 0, 1, 0, 1e-3, 1e-3, 0])
+    np.testing.assert_allclose(f[0], expect, atol=1e-7)
+    np.testing.assert_allclose(f[1], expect, atol=1e-7)
+    assert (f[2] == 0).all()
+    assert (pgeof.compute_features(xyz, nn, nn_ptr, 2)[0] == 0).all()
+    b200.set_eig_order("documented")
+    rng = np.random.default_rng(12)
+    plane = np.c_[rng.uniform(0, 1, (40, 2)), np.full(40, 0.5)].astype(np.float32)
+    f = pgeof.compute_features(plane, np.arange(40, dtype=np.uint32), np.array([0, 40], np.uint32))[0]
+    np.testing.assert_allclose(f[4:7], [0, 0, 1], atol=1e-6)
+    assert abs(f[2]) < 1e-6 and abs(f[10]) < 1e-6
+    with pytest.raises(IndexError):                                                 # reference: UB (pca.hpp:124-126)
+        pgeof.compute_features(xyz, np.array([0, 9], np.uint32), np.array([0, 2], np.uint32))
+    with pytest.raises(IndexError):
+        pgeof.compute_features(xyz, nn, np.array([0, 9], np.uint32))
+    assert pgeof.compute_features(xyz, nn[:0], np.zeros(1, np.uint32)).shape == (0, 11)
+
+
+@pytest.mark.parametrize("order", ORDERS)
+def test_multiscale_c4_shape(order):
+    """BASELINE config 4 shape: k_scales = [10, 20, 50, 100] from one k = 100 kNN pass (60k points here)."""
+    b200.set_eig_order(order)
+    xyz = synth.uniform_cloud(60000, seed=13)
+    idx, _ = pgeof.knn_search(xyz, xyz, 100)
+    nn, nn_ptr = knn_csr(idx)
+    scales = [10, 20, 50, 100]
+    ms = pgeof.compute_features_multiscale(xyz, nn, nn_ptr, scales)
+    ref = cpu.compute_features_multiscale(xyz, nn, nn_ptr, scales, order)
+    assert ms.shape == (60000, 4, 11)
+    for s, ks in enumerate(scales):
+        compare_features(ms[:, s], ref[:, s], row_eigvals_dense(xyz, idx[:, :ks]), order, "scale %d" % ks)
+    # the last scale is the whole row: bitwise the same code path as compute_features
+    np.testing.assert_array_equal(ms[:, 3], pgeof.compute_features(xyz, nn, nn_ptr))
+
+
+def test_multiscale_ragged_rows_many_scales_and_inputs():
+    xyz = synth.lidar_like_cloud(50000, seed=3)
+    idx, _ = pgeof.radius_search(xyz, xyz, 0.4, 40)
+    nn, nn_ptr = radius_csr(idx)
+    scales = [1, 2, 3, 5, 8, 8, 13, 21, 30, 40, 64]                                  # > 8 scales: two passes; a duplicate; one never reached
+    ms = pgeof.compute_features_multiscale(xyz, nn, nn_ptr, np.asarray(scales, np.int64))
+    ref = cpu.compute_features_multiscale(xyz, nn, nn_ptr, scales)
+    lens = np.diff(nn_ptr.astype(np.int64))
+    for s, ks in enumerate(scales):
+        assert (ms[lens < ks, s] == 0).all()                                         # early break, pgeof.hpp:193
+        compare_features(ms[:, s], ref[:, s], row_eigvals(xyz, nn, nn_ptr, ks), "literal", "scale %d" % ks)
+    assert (ms[:, -1] == 0).all()
+
+
+@pytest.mark.parametrize("k_min,k_step,k_min_search", [(1, 1, 10), (1, 1, 1), (5, 3, 10), (20, 7, 4), (1, 200, 10)])
+def test_optimal_k_exact(k_min, k_step, k_min_search):
+    """BASELINE config 5 shape (k = 100, scan from k_min_search) on 30k points: k_opt must be exact."""
+    xyz = synth.uniform_cloud(30000, seed=14)
+    idx, _ = pgeof.knn_search(xyz, xyz, 100)
+    nn, nn_ptr = knn_csr(idx)
+    opt = pgeof.compute_features_optimal(xyz, nn, nn_ptr, k_min, k_step, k_min_search)
+    ref, margin = cpu.compute_features_optimal(xyz, nn, nn_ptr, k_min, k_step, k_min_search, return_margin=True)
+    assert opt.shape == (30000, 12) and opt.dtype == np.float32
+    sure = margin > 1e-9        # below that two neighbourhood sizes tie in float64 itself
+    assert sure.mean() > 0.999
+    np.testing.assert_array_equal(opt[sure, 11], ref[sure, 11])
+    rows = np.nonzero(sure)[0]
+    kopt = ref[rows, 11].astype(int)
+    ev = np.stack([np.linalg.eigvalsh(np.cov(xyz[idx[r, :k]].astype(np.float64).T, bias=True)) for r, k in zip(rows[:3000], kopt[:3000])])
+    compare_features(opt[rows[:3000], :11], ref[rows[:3000], :11], ev, "literal", "optimal features")
+
+
+def test_optimal_ragged_rows_and_gates():
+    xyz = synth.lidar_like_cloud(40000, seed=4)
+    idx, _ = pgeof.radius_search(xyz, xyz, 0.35, 60)
+    nn, nn_ptr = radius_csr(idx)
+    opt = pgeof.compute_features_optimal(xyz, nn, nn_ptr, 3, 2, 6)
+    ref, margin = cpu.compute_features_optimal(xyz, nn, nn_ptr, 3, 2, 6, return_margin=True)
+    lens = np.diff(nn_ptr.astype(np.int64))
+    assert (opt[lens < 6] == 0).all()                                                # pgeof.hpp:272
+    sure = margin > 1e-9
+    np.testing.assert_array_equal(opt[sure, 11], ref[sure, 11])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("order", ORDERS)
+def test_selected_fused_radius_features(dtype, order):
+    b200.set_eig_order(order)
+    E = pgeof.EFeatureID
+    ids = [E.Verticality, E.Curvature, E.Eigentropy, E.K_optimal, E.Linearity, E.Planarity, E.Scattering, E.VerticalityPGEOF,
+           E.Normal_x, E.Normal_y, E.Normal_z, E.Length, E.Surface, E.Volume]
+    xyz = (np.random.default_rng(15).random((20000, 3)) * (1 + 1e-9)).astype(dtype)
+    for r, max_knn in ((0.06, 50), (0.08, 12), (0.02, 30)):                          # full balls, truncated balls, mostly < 2 points
+        out = pgeof.compute_features_selected(xyz, r, max_knn, ids)
+        assert out.dtype == dtype and out.shape == (20000, len(ids))
+        ref = cpu.compute_features_selected(xyz, r, max_knn, [int(i) for i in ids], order)
+        # neighbourhoods (in the metric of the dtype) for the conditioning masks
+        tree_idx, _ = cpu.radius_search(xyz.astype(np.float32), xyz.astype(np.float32), r, max_knn)
+        nn, nn_ptr = radius_csr(tree_idx)
+        lone = np.diff(nn_ptr.astype(np.int64)) < 2
+        if dtype == np.float32:
+            assert (out[lone] == 0).all()                                            # pgeof.hpp:355
+        compare_features(out, ref, row_eigvals(xyz, nn, nn_ptr), order, "selected r=%g" % r, [int(i) for i in ids])
+
+
+def test_selected_bench_jakteristics_shape_and_ties():
+    """tests/bench_jakteristics.py:12-45 workload (10k float64 pts in [0,200)^3, r=5, max_knn=50, Verticality)."""
+    xyz = np.random.default_rng(16).uniform(0.0, 200.0, size=(10000, 3))
+    out = pgeof.compute_features_selected(xyz, 5.0, 50, [pgeof.EFeatureID.Verticality])
+    ref = cpu.compute_features_selected(xyz, 5.0, 50, [12])
+    assert out.shape == (10000, 1) and np.abs(out - ref).max() < 1e-6 or np.mean(np.abs(out - ref) > 1e-6) < 0.01
+    # lattice: exact-distance ties at the max_knn boundary must resolve by index like the oracle (eigenvalue columns)
+    g = np.stack(np.meshgrid(*[np.arange(10)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    for dtype in (np.float32, np.float64):
+        lat = g.astype(dtype)
+        ids = [7, 8, 10, 13]
+        out = pgeof.compute_features_selected(lat, 1.5, 9, ids)
+        ref = cpu.compute_features_selected(lat, 1.5, 9, ids, "literal")
+        np.testing.assert_allclose(out, ref, atol=2e-4, rtol=2e-3)
+
+
+# --------------------------------------------------------------------------------------------
+# device tensors (DLPack / torch CUDA) and the raw C ABI
+# --------------------------------------------------------------------------------------------
+def test_torch_cuda_tensors_match_numpy_path():
+    import torch
+    xyz = synth.uniform_cloud(50000, seed=17)
+    t = torch.from_numpy(xyz).cuda()
+    idx_np, d2_np = pgeof.knn_search(xyz, xyz, 24)
+    idx_t, d2_t = pgeof.knn_search(t, t, 24)
+    assert idx_t.is_cuda and idx_t.dtype == torch.uint32 and d2_t.dtype == torch.float32
+    np.testing.assert_array_equal(idx_t.cpu().numpy(), idx_np)
+    np.testing.assert_array_equal(d2_t.cpu().numpy(), d2_np)
+    nn_ptr = (torch.arange(50001, device="cuda") * 24).to(torch.uint32)
+    f_t = pgeof.compute_features(t, idx_t.view(-1), nn_ptr)                          # zero-copy CSR view
+    nn, ptr = knn_csr(idx_np)
+    np.testing.assert_array_equal(f_t.cpu().numpy(), pgeof.compute_features(xyz, nn, ptr))
+    r_t = pgeof.radius_search(t, t[:1000], 9.0, 16)
+    r_np = pgeof.radius_search(xyz, xyz[:1000], 9.0, 16)
+    np.testing.assert_array_equal(r_t[0].cpu().numpy(), r_np[0])
+    fused = b200.knn_features(t, 24)
+    np.testing.assert_array_equal(fused.cpu().numpy(), f_t.cpu().numpy())
+    with pytest.raises(TypeError):
+        pgeof.knn_search(t, xyz, 4)                                                  # mixed memory spaces
+    with pytest.raises(TypeError):
+        pgeof.knn_search(t.double(), t.double(), 4)
+    assert b200.launch_count() > 0
+
+
+def test_c_abi_called_directly_through_ctypes():
+    """What a non-Python FFI (cgo / JNI stub of INTEGRATION.md) would do: plain pointers and sizes."""
+    lib = ctypes.CDLL(b200.LIBRARY_PATH)
+    lib.pgeof_last_error.restype = ctypes.c_char_p
+    xyz = synth.uniform_cloud(5000, seed=18)
+    k = 16
+    idx = np.empty((5000, k), np.uint32)
+    d2 = np.empty((5000, k), np.float32)
+    vp = ctypes.c_void_p
+    rc = lib.pgeof_knn_search(xyz.ctypes.data_as(vp), ctypes.c_size_t(5000), xyz.ctypes.data_as(vp), ctypes.c_size_t(5000),
+                              ctypes.c_uint32(k), idx.ctypes.data_as(vp), d2.ctypes.data_as(vp))
+    assert rc == 0, lib.pgeof_last_error()
+    _assert_search_equal((idx, d2), cpu.knn_search(xyz, xyz, k))
+    nn, nn_ptr = knn_csr(idx)
+    out = np.empty((5000, 11), np.float32)
+    rc = lib.pgeof_compute_features(xyz.ctypes.data_as(vp), ctypes.c_size_t(5000), nn.ctypes.data_as(vp), ctypes.c_size_t(len(nn)),
+                                    nn_ptr.ctypes.data_as(vp), ctypes.c_size_t(5000), ctypes.c_uint32(1), ctypes.c_int(0), out.ctypes.data_as(vp))
+    assert rc == 0, lib.pgeof_last_error()
+    compare_features(out, cpu.compute_features(xyz, nn, nn_ptr), row_eigvals_dense(xyz, idx))
+    rc = lib.pgeof_knn_search(xyz.ctypes.data_as(vp), ctypes.c_size_t(5000), xyz.ctypes.data_as(vp), ctypes.c_size_t(5000),
+                              ctypes.c_uint32(5001), idx.ctypes.data_as(vp), d2.ctypes.data_as(vp))
+    assert rc == -1 and b"knn size" in lib.pgeof_last_error()                        # PGEOF_EINVAL
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE full size (10M points, k = 50): size-independent properties + sampled oracle rows
+# --------------------------------------------------------------------------------------------
+def test_metric_workload_full_size_properties():
+    import torch
+    n, k = 10_000_000, 50
+    xyz = synth.uniform_cloud(n, seed=0)
+    t = torch.from_numpy(xyz).cuda()
+    idx, d2 = pgeof.knn_search(t, t, k)
+    nn_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int64) * k).to(torch.uint32)
+    feats = pgeof.compute_features(t, idx.view(-1), nn_ptr)
+    torch.cuda.synchronize()
+    # sortedness, self-first, index range -- on the device
+    d2f = d2.view(n, k)
+    assert bool((d2f[:, 1:] >= d2f[:, :-1]).all())
+    idx64 = idx.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    assert bool((idx64[:, 0] == torch.arange(n, device="cuda")).all()) and bool((d2f[:, 0] == 0).all())
+    assert int(idx64.max()) < n
+    # checksum of recomputed distances: d2 must be exactly the defined float32 metric of the returned indices
+    rows = torch.from_numpy(np.random.default_rng(3).choice(n, 200000, replace=False)).cuda()
+    p = t[idx64[rows]]                                  # (m, k, 3)
+    q = t[rows][:, None, :]
+    diff = q - p
+    re = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+    assert bool((re == d2f[rows]).all())
+    # sampled rows against the oracle run over the full 10M cloud
+    sample = np.random.default_rng(4).choice(n, 512, replace=False)
+    ref = cpu.knn_search(xyz, xyz[sample], k, brute=True)
+    s = torch.from_numpy(sample).cuda()
+    _assert_search_equal((idx64[s].cpu().numpy().astype(np.uint32), d2f[s].cpu().numpy()), ref)
+    nn = ref[0].reshape(-1)
+    fref = cpu.compute_features(xyz, nn, (np.arange(513) * k).astype(np.uint32))
+    compare_features(feats[s].cpu().numpy(), fref, row_eigvals_dense(xyz, ref[0]))
+    assert bool(torch.isfinite(feats).all())
