@@ -27,7 +27,7 @@ void set_error(const char* fmt, ...)
 // ---------------------------------------------------------------------------
 // optional per-kernel event timing
 // ---------------------------------------------------------------------------
-static const char* const kTimerNames[] = {"knn_search", "radius_search", "features", "multiscale", "optimal", "selected", "grid_build"};
+static const char* const kTimerNames[] = {"knn_search", "radius_search", "features", "multiscale", "optimal", "selected", "grid_build", "row_order"};
 constexpr int kNumTimers = sizeof(kTimerNames) / sizeof(kTimerNames[0]);
 static bool g_profile = false;
 static std::mutex g_profile_mutex;

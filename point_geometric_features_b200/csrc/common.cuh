@@ -113,6 +113,9 @@ int selected_run_f32(const float* xyz, size_t n, float radius, uint32_t max_knn,
 int selected_run_f64(const double* xyz, size_t n, double radius, uint32_t max_knn, const int32_t* ids_host, size_t n_ids,
                      int eig_order, double* out, cudaStream_t stream);
 
+// per-block bounding boxes of an (n,3) cloud: out[b*6 + {0..2}] = min, out[b*6 + {3..5}] = max
+int bbox_partials(const float* xyz, size_t n, DeviceBuffer* out, int* n_partials, cudaStream_t stream);
+
 // exclusive scan of `n` uint32 counts in place; writes the grand total to data[n]
 int exclusive_scan_u32(uint32_t* data, size_t n, cudaStream_t stream);
 

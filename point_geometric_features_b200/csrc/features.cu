@@ -2,18 +2,29 @@
 // Replaces compute_geometric_features{,_multiscale,_optimal} (include/pgeof.hpp:75-310)
 // and pca_from_neighborhood / pca_from_pointcloud (include/pca.hpp:71-129).
 //
-// Layout: one CTA owns a tile of kRows consecutive CSR rows.  The tile's slice of `nn`
-// is one contiguous span, so it is staged into shared memory with a single 1-D TMA bulk
-// copy (cp.async.bulk + mbarrier) when 16-B alignment allows, else with coalesced loads.
-// Then ONE THREAD PER ROW walks its neighbour list: gathers xyz (3 x 4-B read-only loads,
-// several rows of loads in flight per thread), accumulates the 9 origin-shifted moments
-// (origin = the row's first neighbour), solves the 3x3 eigenproblem in
-// registers (eig3.cuh) and stages its 11 floats in shared memory; the tile's output is one
-// contiguous block written with a TMA bulk store (or coalesced stores).
+// Layout.  Rows are processed in SPATIAL order: a counting sort of the rows by the coarse
+// cell of their first neighbour (row_order_*) makes consecutive threads / CTAs work on
+// overlapping neighbourhoods, so the xyz gathers of a row hit lines its spatial neighbours
+// just pulled into L1 / L2 instead of a random 32-B DRAM sector each (the first version read
+// 25.8 GB from DRAM for 8.5 GB of algorithmic bytes, profiles/r1a_summary.md).  The cloud is
+// re-packed once into 16-B float4 records so that a gather is ONE 128-bit load.
+// One CTA owns kRows rows, ONE THREAD PER ROW:
+//   stage   the rows' slices of `nn` go to shared memory -- permuted rows: per-warp cp.async
+//           (LDGSTS) of each row's contiguous slice; identity order (small inputs): the whole
+//           tile is one contiguous span moved by a single 1-D TMA bulk copy (cp.async.bulk +
+//           mbarrier) when 16-B alignment allows;
+//   walk    each thread walks its neighbour list in shared memory, gathers float4 points with
+//           several loads in flight, accumulates the 9 origin-shifted moments (origin = the
+//           row's first neighbour), solves the 3x3 eigenproblem in registers
+//           (eig3.cuh) and derives the features;
+//   store   the tile's features are staged in shared memory and written as 44-B row segments
+//           (permuted) or one TMA bulk store (identity order).
 //
 // Algorithmic bytes per row of length k: 4k (nn) + 4 (nn_ptr) + 12k (xyz gather) + 44 (out)
-// = 48 + 16k; HBM-bound (random 12-B gathers cost a 32-B sector each).
+// = 48 + 16k.
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "eig3.cuh"
@@ -29,6 +40,8 @@ constexpr int kMaxScalesPerPass = 8;
 
 struct FeatArgs {
     const float* xyz; uint32_t n_xyz;
+    const float4* xyz4;           // 16-B padded copy of xyz (one LDG.128 per gather)
+    const uint32_t* order;        // spatial row permutation, or nullptr = identity
     const uint32_t* nn; uint32_t nnz;
     const uint32_t* nn_ptr; uint32_t n_rows;
     uint32_t k_min; int eig_order;
@@ -77,58 +90,124 @@ struct MomentsD {
     }
 };
 
-// Tile prologue shared by the three kernels: stages nn[p0, p1) of the CTA's rows.
-// Returns the tile-relative base (entry p lives at s_nn[p - a0]) or staged = false.
-struct Tile {
-    uint32_t r0, rows, p0, p1, a0;
-    bool staged, ok;
+// Per-thread view of its row after staging.
+struct Row {
+    uint32_t row;      // CSR row handled by this thread
+    uint32_t b, len;   // nn[b, b + len)
+    uint32_t s_off;    // offset of the slice inside the shared-memory tile (when staged)
+    bool staged;       // slice lives in shared memory (else read nn from global)
+    bool valid;        // thread owns a well-formed row
 };
 
-__device__ __forceinline__ Tile stage_tile(const FeatArgs& a, uint32_t* s_nn, uint64_t* bar)
+struct Tile {
+    uint32_t r0, rows;   // positions [r0, r0 + rows) of the (permuted) row sequence
+    bool bulk_store;     // identity order: the tile's output is one contiguous block
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t* smem_dst, const uint32_t* gmem_src)
 {
-    Tile t;
-    t.r0 = blockIdx.x * kRows;
-    t.rows = min((uint32_t)kRows, a.n_rows - t.r0);
-    t.p0 = __ldg(a.nn_ptr + t.r0);
-    t.p1 = __ldg(a.nn_ptr + t.r0 + t.rows);
-    t.ok = t.p0 <= t.p1 && t.p1 <= a.nnz;          // corrupt nn_ptr -> PGEOF_EINDEX, rows left 0
-    t.a0 = t.p0 & ~3u;
-    t.staged = t.ok && (t.p1 - t.a0) <= a.nn_cap;
-    if (!t.ok) { if (threadIdx.x == 0) atomicExch(a.err, 1); return t; }
-    if (!t.staged) return t;
-    const uint32_t a1 = max(t.p1 & ~3u, t.a0);     // end of the 16-B aligned body
-    if (a.tma_in && a1 > t.a0) {
-        if (threadIdx.x == 0) {
-            ptx::mbarrier_init(bar, 1);
-            ptx::fence_mbarrier_init();
-            const uint32_t bytes = (a1 - t.a0) * 4u;
-            ptx::mbarrier_arrive_expect_tx(bar, bytes);
-            ptx::bulk_g2s(s_nn, a.nn + t.a0, bytes, bar);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_addr(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Stages the nn slices of the CTA's rows into shared memory and returns this thread's row.
+__device__ __forceinline__ Row stage_rows(const FeatArgs& a, uint32_t* s_nn, uint32_t* s_rowid, uint64_t* bar, Tile* tile)
+{
+    const uint32_t r0 = blockIdx.x * kRows;
+    const uint32_t rows = min((uint32_t)kRows, a.n_rows - r0);
+    tile->r0 = r0; tile->rows = rows; tile->bulk_store = false;
+    Row r{0, 0, 0, 0, false, false};
+    if (a.order) {
+        // ---- permuted rows: every warp stages its own 32 rows with cp.async ---------------
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (threadIdx.x < rows) {
+            r.row = __ldg(a.order + r0 + threadIdx.x);
+            const uint32_t b = __ldg(a.nn_ptr + r.row), e = __ldg(a.nn_ptr + r.row + 1);
+            if (e < b || e > a.nnz) atomicExch(a.err, 1);         // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
+            else { r.b = b; r.len = e - b; r.valid = true; }
         }
-        for (uint32_t p = a1 + threadIdx.x; p < t.p1; p += kRows) s_nn[p - t.a0] = __ldg(a.nn + p);   // <= 3 entries
-        __syncthreads();                      // barrier init visible to the waiters + tail stored
-        ptx::mbarrier_wait(bar, 0);
-    } else {
-        for (uint32_t p = t.p0 + threadIdx.x; p < t.p1; p += kRows) s_nn[p - t.a0] = __ldg(a.nn + p);
-        __syncthreads();
+        s_rowid[threadIdx.x] = r.row;
+        uint32_t inc = r.len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t warp_cap = a.nn_cap / (kRows / 32);
+        r.staged = warp_total <= warp_cap;
+        r.s_off = warp * warp_cap + inc - r.len;
+        if (r.staged) {
+            for (int s = 0; s < 32; ++s) {
+                const uint32_t bs = __shfl_sync(0xffffffffu, r.b, s), ls = __shfl_sync(0xffffffffu, r.len, s);
+                const uint32_t os = __shfl_sync(0xffffffffu, r.s_off, s);
+                for (uint32_t j = lane; j < ls; j += 32) cp_async4(s_nn + os + j, a.nn + bs + j);
+            }
+            cp_async_wait_all();
+            __syncwarp();
+        }
+        return r;
     }
-    return t;
+    // ---- identity order: the tile's nn is one contiguous span -> 1-D TMA bulk copy ---------
+    const uint32_t p0 = __ldg(a.nn_ptr + r0), p1 = __ldg(a.nn_ptr + r0 + rows);
+    const bool ok = p0 <= p1 && p1 <= a.nnz;
+    const uint32_t a0 = p0 & ~3u;
+    const bool staged = ok && (p1 - a0) <= a.nn_cap;
+    tile->bulk_store = true;
+    s_rowid[threadIdx.x] = r0 + threadIdx.x;
+    if (!ok) { if (threadIdx.x == 0) atomicExch(a.err, 1); return r; }
+    if (staged) {
+        const uint32_t a1 = max(p1 & ~3u, a0);     // end of the 16-B aligned body
+        if (a.tma_in && a1 > a0) {
+            if (threadIdx.x == 0) {
+                ptx::mbarrier_init(bar, 1);
+                ptx::fence_mbarrier_init();
+                const uint32_t bytes = (a1 - a0) * 4u;
+                ptx::mbarrier_arrive_expect_tx(bar, bytes);
+                ptx::bulk_g2s(s_nn, a.nn + a0, bytes, bar);
+            }
+            for (uint32_t p = a1 + threadIdx.x; p < p1; p += kRows) s_nn[p - a0] = __ldg(a.nn + p);   // <= 3 entries
+            __syncthreads();                      // barrier init visible to the waiters + tail stored
+            ptx::mbarrier_wait(bar, 0);
+        } else {
+            for (uint32_t p = p0 + threadIdx.x; p < p1; p += kRows) s_nn[p - a0] = __ldg(a.nn + p);
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x < rows) {
+        r.row = r0 + threadIdx.x;
+        const uint32_t b = __ldg(a.nn_ptr + r.row), e = __ldg(a.nn_ptr + r.row + 1);
+        if (e < b || e > a.nnz) atomicExch(a.err, 1);
+        else { r.b = b; r.len = e - b; r.valid = true; r.staged = staged; r.s_off = b - a0; }
+    }
+    return r;
 }
 
-__device__ __forceinline__ void store_tile(const FeatArgs& a, const Tile& t, const float* s_out, uint32_t floats_per_row, float* gdst)
+// Writes the tile's staged features: F floats per row.
+template <int F>
+__device__ __forceinline__ void store_rows(const FeatArgs& a, const Tile& t, const float* s_out, const uint32_t* s_rowid)
 {
     __syncthreads();
-    const uint32_t total = t.rows * floats_per_row;
-    if (a.tma_out && (total & 3u) == 0) {
+    const uint32_t total = t.rows * F;
+    if (t.bulk_store && a.tma_out && (total & 3u) == 0) {
         if (threadIdx.x == 0) {
             ptx::fence_proxy_async_smem();
-            ptx::bulk_s2g(gdst, s_out, total * 4u);
+            ptx::bulk_s2g(a.out + (size_t)t.r0 * F, s_out, total * 4u);
             ptx::bulk_commit();
             ptx::bulk_wait_read0();
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < total; i += kRows) gdst[i] = s_out[i];
+        for (uint32_t i = threadIdx.x; i < total; i += kRows) {
+            const uint32_t r = i / F, f = i - r * F;
+            a.out[(size_t)s_rowid[r] * F + f] = s_out[i];
+        }
     }
+}
+
+__device__ __forceinline__ float3 load_point(const FeatArgs& a, uint32_t i)
+{
+    if (a.xyz4) { const float4 p = __ldg(a.xyz4 + i); return make_float3(p.x, p.y, p.z); }
+    return make_float3(__ldg(a.xyz + 3 * (size_t)i), __ldg(a.xyz + 3 * (size_t)i + 1), __ldg(a.xyz + 3 * (size_t)i + 2));
 }
 
 // row walker: calls fn(j, dx, dy, dz) for neighbour j = 0..len-1 with coordinates
@@ -138,21 +217,35 @@ __device__ __forceinline__ bool walk_row(const FeatArgs& a, NnPtr src, uint32_t 
 {
     const uint32_t i0 = src[0];
     if (i0 >= a.n_xyz) return false;
-    const float px = __ldg(a.xyz + 3 * (size_t)i0), py = __ldg(a.xyz + 3 * (size_t)i0 + 1), pz = __ldg(a.xyz + 3 * (size_t)i0 + 2);
+    const float3 o = load_point(a, i0);
     bool ok = true;
 #pragma unroll 4
     for (uint32_t j = 0; j < len; ++j) {
         uint32_t i = src[j];
         if (i >= a.n_xyz) { ok = false; i = i0; }
-        const float x = __ldg(a.xyz + 3 * (size_t)i), y = __ldg(a.xyz + 3 * (size_t)i + 1), z = __ldg(a.xyz + 3 * (size_t)i + 2);
-        fn(j, x - px, y - py, z - pz);
+        const float3 p = load_point(a, i);
+        fn(j, p.x - o.x, p.y - o.y, p.z - o.z);
     }
     return ok;
 }
 
-struct GlobalNn {   // fallback when the tile does not fit shared memory
+struct GlobalNn {   // fallback when the slice does not fit shared memory
     const uint32_t* p;
     __device__ __forceinline__ uint32_t operator[](uint32_t j) const { return __ldg(p + j); }
+};
+
+template <typename Fn>
+__device__ __forceinline__ bool walk(const FeatArgs& a, const Row& r, const uint32_t* s_nn, uint32_t len, Fn&& fn)
+{
+    return r.staged ? walk_row(a, s_nn + r.s_off, len, fn) : walk_row(a, GlobalNn{a.nn + r.b}, len, fn);
+}
+
+// shared-memory carve-up: [0,128) mbarrier | s_rowid[kRows] | s_out[kRows * F] | s_nn[nn_cap]
+template <int F>
+struct Smem {
+    static constexpr size_t kRowId = 128;
+    static constexpr size_t kOut = kRowId + kRows * sizeof(uint32_t);
+    static constexpr size_t kNn = kOut + (size_t)kRows * F * sizeof(float);
 };
 
 // ----------------------------------------------------------------------------------
@@ -162,29 +255,23 @@ __global__ void __launch_bounds__(kRows) features_kernel(const FeatArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    float* s_out = reinterpret_cast<float*>(smem + 128);
-    uint32_t* s_nn = reinterpret_cast<uint32_t*>(smem + 128 + kRows * 11 * sizeof(float));
-    const Tile t = stage_tile(a, s_nn, bar);
+    uint32_t* s_rowid = reinterpret_cast<uint32_t*>(smem + Smem<11>::kRowId);
+    float* s_out = reinterpret_cast<float*>(smem + Smem<11>::kOut);
+    uint32_t* s_nn = reinterpret_cast<uint32_t*>(smem + Smem<11>::kNn);
+    Tile t;
+    const Row r = stage_rows(a, s_nn, s_rowid, bar, &t);
     float f[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) f[i] = 0.f;
-    if (t.ok && threadIdx.x < t.rows) {
-        const uint32_t b = __ldg(a.nn_ptr + t.r0 + threadIdx.x), e = __ldg(a.nn_ptr + t.r0 + threadIdx.x + 1);
-        if (e < b || e > a.nnz) atomicExch(a.err, 1);
-        else {
-            const uint32_t len = e - b;
-            if (len >= a.k_min && len > 0) {          // pgeof.hpp:103
-                Moments m;
-                auto acc = [&](uint32_t, float dx, float dy, float dz) { m.add(dx, dy, dz); };
-                const bool ok = t.staged ? walk_row(a, s_nn + (b - t.a0), len, acc) : walk_row(a, GlobalNn{a.nn + b}, len, acc);
-                if (!ok) atomicExch(a.err, 2);
-                else features11<float>(m.pca(len, a.eig_order), f);
-            }
-        }
+    if (r.valid && r.len >= a.k_min && r.len > 0) {          // pgeof.hpp:103
+        Moments m;
+        auto acc = [&](uint32_t, float dx, float dy, float dz) { m.add(dx, dy, dz); };
+        if (!walk(a, r, s_nn, r.len, acc)) atomicExch(a.err, 2);
+        else features11<float>(m.pca(r.len, a.eig_order), f);
     }
 #pragma unroll
     for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
-    store_tile(a, t, s_out, 11, a.out + (size_t)t.r0 * 11);
+    store_rows<11>(a, t, s_out, s_rowid);
 }
 
 // ----------------------------------------------------------------------------------
@@ -195,19 +282,17 @@ __global__ void __launch_bounds__(kRows) multiscale_kernel(const FeatArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    uint32_t* s_nn = reinterpret_cast<uint32_t*>(smem + 128);
-    const Tile t = stage_tile(a, s_nn, bar);
-    if (!t.ok || threadIdx.x >= t.rows) return;
-    const uint32_t row = t.r0 + threadIdx.x;
-    const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
-    if (e < b || e > a.nnz) { atomicExch(a.err, 1); return; }
-    const uint32_t len = e - b;
+    uint32_t* s_rowid = reinterpret_cast<uint32_t*>(smem + Smem<0>::kRowId);
+    uint32_t* s_nn = reinterpret_cast<uint32_t*>(smem + Smem<0>::kNn);
+    Tile t;
+    const Row r = stage_rows(a, s_nn, s_rowid, bar, &t);
+    if (!r.valid) return;
     // rows are only walked up to the largest scale of this pass that fits (pgeof.hpp:193 early break)
     uint32_t n_fit = 0;
-    while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
+    while (n_fit < a.n_scales_pass && a.scales[n_fit] <= r.len) ++n_fit;
     if (n_fit == 0 || a.scales[n_fit - 1] == 0) return;
-    const uint32_t walk = a.scales[n_fit - 1];
-    float* out = a.out + ((size_t)row * a.n_scales_total + a.scale_base) * 11;
+    const uint32_t walk_len = a.scales[n_fit - 1];
+    float* out = a.out + ((size_t)r.row * a.n_scales_total + a.scale_base) * 11;
     Moments m;
     uint32_t s = 0;
     while (s < n_fit && a.scales[s] == 0) ++s;   // k_s = 0 is rejected on the host; defensive
@@ -221,8 +306,7 @@ __global__ void __launch_bounds__(kRows) multiscale_kernel(const FeatArgs a)
             ++s;
         }
     };
-    const bool ok = t.staged ? walk_row(a, s_nn + (b - t.a0), walk, acc) : walk_row(a, GlobalNn{a.nn + b}, walk, acc);
-    if (!ok) {
+    if (!walk(a, r, s_nn, walk_len, acc)) {
         atomicExch(a.err, 2);
         for (uint32_t i = 0; i < n_fit * 11; ++i) out[i] = 0.f;
     }
@@ -237,63 +321,134 @@ __global__ void __launch_bounds__(kRows) optimal_kernel(const FeatArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    float* s_out = reinterpret_cast<float*>(smem + 128);
-    uint32_t* s_nn = reinterpret_cast<uint32_t*>(smem + 128 + kRows * 12 * sizeof(float));
-    const Tile t = stage_tile(a, s_nn, bar);
+    uint32_t* s_rowid = reinterpret_cast<uint32_t*>(smem + Smem<12>::kRowId);
+    float* s_out = reinterpret_cast<float*>(smem + Smem<12>::kOut);
+    uint32_t* s_nn = reinterpret_cast<uint32_t*>(smem + Smem<12>::kNn);
+    Tile t;
+    const Row r = stage_rows(a, s_nn, s_rowid, bar, &t);
     float f[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) f[i] = 0.f;
-    if (t.ok && threadIdx.x < t.rows) {
-        const uint32_t b = __ldg(a.nn_ptr + t.r0 + threadIdx.x), e = __ldg(a.nn_ptr + t.r0 + threadIdx.x + 1);
-        if (e < b || e > a.nnz) atomicExch(a.err, 1);
-        else {
-            const uint32_t len = e - b;
-            if (len >= a.k_min && len >= a.k_min_search && len > 0) {               // pgeof.hpp:272
-                const uint32_t k0 = min(max(max(a.k_min, a.k_min_search), 1u), len);   // :274
-                MomentsD m;
-                double best_h = 1.0, best_c[6] = {0, 0, 0, 0, 0, 0};
-                uint32_t best_k = len;
-                auto acc = [&](uint32_t j, float dx, float dy, float dz) {
-                    m.add((double)dx, (double)dy, (double)dz);
-                    const uint32_t k = j + 1;
-                    if (k < k0) return;
-                    if (k > k0 && (k % a.k_step) != 0 && k != len) return;          // :283
-                    double c[6], w[3];
-                    m.cov(k, c);
-                    eigvals3_f64(c[0], c[1], c[2], c[3], c[4], c[5], w);
-                    const double h = eigentropy_of<double>(w[0], w[1], w[2]);
-                    if (k == k0 || h < best_h) {                                    // :289
-                        best_h = h; best_k = k;
+    const uint32_t len = r.len;
+    if (r.valid && len >= a.k_min && len >= a.k_min_search && len > 0) {               // pgeof.hpp:272
+        const uint32_t k0 = min(max(max(a.k_min, a.k_min_search), 1u), len);           // :274
+        MomentsD m;
+        double best_h = 1.0, best_c[6] = {0, 0, 0, 0, 0, 0};
+        uint32_t best_k = len;
+        auto acc = [&](uint32_t j, float dx, float dy, float dz) {
+            m.add((double)dx, (double)dy, (double)dz);
+            const uint32_t k = j + 1;
+            if (k < k0) return;
+            if (k > k0 && (k % a.k_step) != 0 && k != len) return;                      // :283
+            double c[6], w[3];
+            m.cov(k, c);
+            eigvals3_f64(c[0], c[1], c[2], c[3], c[4], c[5], w);
+            const double h = eigentropy_of<double>(w[0], w[1], w[2]);
+            if (k == k0 || h < best_h) {                                                // :289
+                best_h = h; best_k = k;
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) best_c[i] = c[i];
-                    }
-                };
-                const bool ok = t.staged ? walk_row(a, s_nn + (b - t.a0), len, acc) : walk_row(a, GlobalNn{a.nn + b}, len, acc);
-                if (!ok) atomicExch(a.err, 2);
-                else {
-                    float g[11];
-                    features11<float>(pca_from_cov<float>((float)best_c[0], (float)best_c[1], (float)best_c[2], (float)best_c[3],
-                                                         (float)best_c[4], (float)best_c[5], a.eig_order), g);
-#pragma unroll
-                    for (int i = 0; i < 11; ++i) f[i] = g[i];
-                    f[11] = (float)best_k;
-                }
+                for (int i = 0; i < 6; ++i) best_c[i] = c[i];
             }
+        };
+        if (!walk(a, r, s_nn, len, acc)) atomicExch(a.err, 2);
+        else {
+            float g[11];
+            features11<float>(pca_from_cov<float>((float)best_c[0], (float)best_c[1], (float)best_c[2], (float)best_c[3],
+                                                 (float)best_c[4], (float)best_c[5], a.eig_order), g);
+#pragma unroll
+            for (int i = 0; i < 11; ++i) f[i] = g[i];
+            f[11] = (float)best_k;
         }
     }
 #pragma unroll
     for (int i = 0; i < 12; ++i) s_out[threadIdx.x * 12 + i] = f[i];
-    store_tile(a, t, s_out, 12, a.out + (size_t)t.r0 * 12);
+    store_rows<12>(a, t, s_out, s_rowid);
+}
+
+// ----------------------------------------------------------------------------------
+// pre-passes: float4 re-pack of the cloud, spatial ordering of the rows
+// ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pad_xyz_kernel(const float* __restrict__ xyz, size_t n, float4* __restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), 0.f);
+}
+
+struct RowGrid { float lo[3]; float scale[3]; int cells; };
+
+// one warp: reduce the bbox partials and derive the coarse row-ordering grid (no host sync)
+__global__ void row_grid_kernel(const float* __restrict__ partial, int n_partial, int cells, RowGrid* __restrict__ g)
+{
+    const int lane = threadIdx.x;
+    float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int b = lane; b < n_partial; b += 32)
+        for (int d = 0; d < 3; ++d) { mn[d] = fminf(mn[d], partial[b * 6 + d]); mx[d] = fmaxf(mx[d], partial[b * 6 + 3 + d]); }
+    for (int d = 0; d < 3; ++d)
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if (lane == 0) {
+        for (int d = 0; d < 3; ++d) {
+            const float ext = mx[d] - mn[d];
+            g->lo[d] = mn[d];
+            g->scale[d] = (ext > 0.f && ext < 3.0e38f) ? (float)cells / ext : 0.f;
+        }
+        g->cells = cells;
+    }
+}
+
+__device__ __forceinline__ uint32_t row_key(const FeatArgs& a, const RowGrid& g, uint32_t row)
+{
+    const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+    if (e <= b || b >= a.nnz) return 0;
+    const uint32_t i = __ldg(a.nn + b);
+    if (i >= a.n_xyz) return 0;
+    const float4 p = __ldg(a.xyz4 + i);
+    const int c = g.cells;
+    const int cx = min(max(__float2int_rd((p.x - g.lo[0]) * g.scale[0]), 0), c - 1);
+    const int cy = min(max(__float2int_rd((p.y - g.lo[1]) * g.scale[1]), 0), c - 1);
+    const int cz = min(max(__float2int_rd((p.z - g.lo[2]) * g.scale[2]), 0), c - 1);
+    return ((uint32_t)cz * c + cy) * c + cx;
+}
+
+__global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const RowGrid* __restrict__ gp, uint32_t* __restrict__ counts,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ rank)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < a.n_rows;
+    const RowGrid g = *gp;
+    uint32_t key = 0xffffffffu;
+    if (valid) key = row_key(a, g, i);
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned peers = __match_any_sync(active, key);
+    const int leader = __ffs(peers) - 1;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counts + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    unsigned lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+    keys[i] = key;
+    rank[i] = base + (uint32_t)__popc(peers & lt);
+}
+
+__global__ void __launch_bounds__(256) row_scatter_kernel(uint32_t n_rows, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ keys,
+                                                          const uint32_t* __restrict__ rank, uint32_t* __restrict__ order)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rows) order[__ldg(starts + keys[i]) + rank[i]] = i;
 }
 
 // shared-memory tile for `nn`: mean row length with 50 % head-room, at least 32 entries a row
 uint32_t pick_nn_cap(size_t nnz, size_t n_rows, size_t fixed_bytes)
 {
     const double mean = n_rows ? (double)nnz / (double)n_rows : 0.0;
-    size_t cap = (size_t)(kRows * std::max(32.0, mean * 1.5)) + 8;
+    size_t cap = (size_t)(kRows * std::max(32.0, mean * 1.5)) + 16;
     const size_t max_bytes = 96 * 1024 - fixed_bytes;          // keep >= 2 CTAs per SM
     cap = std::min(cap, max_bytes / 4);
-    return (uint32_t)(cap & ~(size_t)3);
+    return (uint32_t)(cap & ~(size_t)15);                      // per-warp quarter stays 16-B aligned
 }
 
 int make_args(FeatArgs* a, const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
@@ -306,6 +461,55 @@ int make_args(FeatArgs* a, const float* xyz, size_t n_xyz, const uint32_t* nn, s
     a->eig_order = eig_order; a->out = out; a->err = err; a->k_min = 1; a->k_step = 1; a->k_min_search = 1;
     a->tma_in = ((uintptr_t)nn % 16 == 0);
     a->tma_out = ((uintptr_t)out % 16 == 0) && ((kRows * floats_per_row * 4) % 16 == 0);
+    return PGEOF_OK;
+}
+
+// Device buffers of the two pre-passes; they live until the feature kernel was enqueued
+// (stream-ordered frees).
+struct Prepass {
+    DeviceBuffer xyz4, order;
+};
+
+int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+int prepare(FeatArgs* a, Prepass* p, cudaStream_t stream)
+{
+    // 1. float4 re-pack of the cloud: one 128-bit load per gathered neighbour
+    PGEOF_TRY(p->xyz4.alloc((size_t)std::max<uint32_t>(a->n_xyz, 1) * sizeof(float4), stream));
+    if (a->n_xyz) {
+        pad_xyz_kernel<<<(a->n_xyz + 255) / 256, 256, 0, stream>>>(a->xyz, a->n_xyz, p->xyz4.as<float4>());
+        PGEOF_LAUNCH_CHECK();
+    }
+    a->xyz4 = p->xyz4.as<float4>();
+    // 2. spatial row order (counting sort by the coarse cell of the first neighbour)
+    const int min_rows = env_int("PGEOF_FEATURES_SORT_MIN_ROWS", 32768);
+    if (a->n_xyz == 0 || a->nnz == 0 || (int64_t)a->n_rows < (int64_t)min_rows || env_int("PGEOF_FEATURES_SORT", 1) == 0) return PGEOF_OK;
+    KernelTimer timer("row_order", stream);
+    DeviceBuffer partial, grid, counts, keys, rank;
+    int n_partial = 0;
+    PGEOF_TRY(bbox_partials(a->xyz, a->n_xyz, &partial, &n_partial, stream));
+    int cells = (int)std::lround(std::cbrt((double)a->n_rows / 6.0));
+    cells = std::min(std::max(cells, 8), 160);
+    const size_t n_cells = (size_t)cells * cells * cells;
+    PGEOF_TRY(grid.alloc(sizeof(RowGrid), stream));
+    PGEOF_TRY(counts.alloc((n_cells + 1) * sizeof(uint32_t), stream));
+    PGEOF_TRY(keys.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
+    PGEOF_TRY(rank.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
+    PGEOF_TRY(p->order.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
+    row_grid_kernel<<<1, 32, 0, stream>>>(partial.as<float>(), n_partial, cells, grid.as<RowGrid>());
+    PGEOF_LAUNCH_CHECK();
+    PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, (n_cells + 1) * sizeof(uint32_t), stream));
+    const unsigned blocks = (a->n_rows + 255) / 256;
+    row_count_kernel<<<blocks, 256, 0, stream>>>(*a, grid.as<RowGrid>(), counts.as<uint32_t>(), keys.as<uint32_t>(), rank.as<uint32_t>());
+    PGEOF_LAUNCH_CHECK();
+    PGEOF_TRY(exclusive_scan_u32(counts.as<uint32_t>(), n_cells, stream));
+    row_scatter_kernel<<<blocks, 256, 0, stream>>>(a->n_rows, counts.as<uint32_t>(), keys.as<uint32_t>(), rank.as<uint32_t>(), p->order.as<uint32_t>());
+    PGEOF_LAUNCH_CHECK();
+    a->order = p->order.as<uint32_t>();
     return PGEOF_OK;
 }
 
@@ -344,7 +548,9 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
     FeatArgs a;
     PGEOF_TRY(make_args(&a, xyz, n_xyz, nn, nnz, nn_ptr, n_rows, eig_order, out, err.as<int>(), 11));
     a.k_min = k_min;
-    const size_t fixed = 128 + kRows * 11 * sizeof(float);
+    Prepass pre;
+    PGEOF_TRY(prepare(&a, &pre, stream));
+    const size_t fixed = Smem<11>::kNn;
     a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
     PGEOF_TRY(launch_tiles(features_kernel, "features", a, fixed + (size_t)a.nn_cap * 4, stream));
     return device_flag_check(err.as<int>(), stream, "compute_features");
@@ -363,7 +569,9 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
     FeatArgs a;
     PGEOF_TRY(make_args(&a, xyz, n_xyz, nn, nnz, nn_ptr, n_rows, eig_order, out, err.as<int>(), 11));
     a.n_scales_total = (uint32_t)n_scales;
-    const size_t fixed = 128;
+    Prepass pre;
+    PGEOF_TRY(prepare(&a, &pre, stream));
+    const size_t fixed = Smem<0>::kNn;
     a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
     for (size_t base = 0; base < n_scales; base += kMaxScalesPerPass) {
         a.scale_base = (uint32_t)base;
@@ -385,7 +593,9 @@ int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, siz
     FeatArgs a;
     PGEOF_TRY(make_args(&a, xyz, n_xyz, nn, nnz, nn_ptr, n_rows, eig_order, out, err.as<int>(), 12));
     a.k_min = k_min; a.k_step = k_step; a.k_min_search = k_min_search;
-    const size_t fixed = 128 + kRows * 12 * sizeof(float);
+    Prepass pre;
+    PGEOF_TRY(prepare(&a, &pre, stream));
+    const size_t fixed = Smem<12>::kNn;
     a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
     PGEOF_TRY(launch_tiles(optimal_kernel, "optimal", a, fixed + (size_t)a.nn_cap * 4, stream));
     return device_flag_check(err.as<int>(), stream, "compute_features_optimal");

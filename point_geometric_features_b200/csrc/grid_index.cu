@@ -159,6 +159,15 @@ __global__ void __launch_bounds__(kThreads) scan_apply(uint32_t* __restrict__ da
 
 }  // namespace
 
+int bbox_partials(const float* xyz, size_t n, DeviceBuffer* out, int* n_partials, cudaStream_t stream)
+{
+    PGEOF_TRY(out->alloc(kBBoxBlocks * 6 * sizeof(float), stream));
+    bbox_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(xyz, n, out->as<float>());
+    PGEOF_LAUNCH_CHECK();
+    *n_partials = kBBoxBlocks;
+    return PGEOF_OK;
+}
+
 int exclusive_scan_u32(uint32_t* data, size_t n, cudaStream_t stream)
 {
     if (n == 0) { PGEOF_CUDA(cudaMemsetAsync(data, 0, sizeof(uint32_t), stream)); return PGEOF_OK; }

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
         float Rg = R, Rg_hi = 0.f;
         u64 tau_lo = 0, tau_hi = 0;
         bool have_lo = false, have_hi = false;
+        int shrinks = 0;
         tau = tau_from_radius(R);
         for (int it = 0; it < 512; ++it) {
             c = scan_ball<CAP, true>(g, qx, qy, qz, Rg, tau, keybuf, lane);
@@ -79,11 +80,16 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
                 }
             } else if (c > (uint32_t)CAP) {
                 tau_hi = tau; have_hi = true; Rg_hi = Rg;
-                if (have_lo) { tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
-                else {
-                    const float f = fminf(fmaxf(cbrtf(a.target / (float)c), 0.3f), 0.9f);
-                    R *= f; Rg = R; tau = tau_from_radius(R);
+                // dense spot: shrink the ball by the density estimate (twice at most) ...
+                bool shrunk = false;
+                if (!have_lo && shrinks < 2) {
+                    const float Rn = R * fminf(fmaxf(cbrtf(a.target / (float)c), 0.3f), 0.9f);
+                    const u64 tn = tau_from_radius(Rn);
+                    if (tn < tau_hi && (tn >> 32) != 0) { R = Rn; Rg = R; tau = tn; ++shrinks; shrunk = true; }
                 }
+                // ... else bisect the key space between tau_lo (0: nothing is below it) and tau_hi:
+                // always converges because keys are distinct (many duplicates / exact ties land here)
+                if (!shrunk) { have_lo = true; tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
             } else break;
         }
     } else {

@@ -57,7 +57,9 @@ def compare_features(got, ref, evals, eig_order="literal", what="features", ids=
       * vector-valued columns (normal, both verticalities) on rows whose relative eigen-gap is
         below 1e-3 -- the eigenvectors are not determined to the tolerance there;
       * the normal's sign on rows with |n_z| < 1e-3 (the z >= 0 canonicalisation is a coin flip);
-      * rank-deficient rows (see ``degenerate``): only a loose 1e-2 check in documented order.
+      * rank-deficient rows (see ``degenerate``): only a loose 1e-2 check in documented order;
+      * literal order: rows whose smallest eigenvalue is below float32 covariance resolution get a
+        tolerance scaled by the predicted amplification (see the comment in the code).
     """
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
@@ -78,6 +80,18 @@ def compare_features(got, ref, evals, eig_order="literal", what="features", ids=
         for c in (cx, cy, cz):
             alt = np.abs(got[:, c] + ref[:, c]) <= ATOL + RTOL * np.abs(ref[:, c])
             bad[flat, c] &= ~alt[flat]
+    if eig_order == "literal":
+        # Literal order puts sqrt(lambda_min) in the 1/(s0 + 1e-3) denominator.  A float32 covariance
+        # carries ~1e-7 lambda_max of absolute error, i.e. d(s0) ~ 1e-7 lambda_max / (2 s0), which the
+        # ratio features amplify by 1/(s0 + 1e-3): rows where that predicted relative error exceeds the
+        # tolerance cannot agree between ANY two float32 evaluations (the reference's own included).
+        s0 = np.sqrt(np.maximum(evals[:, 0], 1e-300))
+        amp = 1e-7 * evals[:, 2] / (2.0 * s0 * (s0 + 1e-3))
+        weak = amp > 1e-4
+        loose_lit = np.abs(got - ref) > 1e-3 + np.minimum(100.0 * amp, 0.5)[:, None] * (np.abs(ref) + 1.0)
+        for fid in (0, 1, 2, 10, 7, 8, 9):
+            for c in col.get(fid, []):
+                bad[weak, c] = loose_lit[weak, c]
     if eig_order == "documented":
         loose = np.abs(got - ref) > 1e-2 + 1e-2 * np.abs(ref)
         for fid in (3, 4, 5, 6, 12):
