@@ -69,8 +69,11 @@ struct DeviceBuffer {
 // ---------------------------------------------------------------------------
 struct GridView {
     float lo[3];          // bbox minimum
-    float h;              // cell edge
+    float h;              // cell edge along y and z
     float inv_h;          // fl(1/h)
+    float hx;             // cell edge along x = h / xf (finer: x-runs are trimmed at this granularity)
+    float inv_hx;         // fl(1/hx)
+    int xf;               // x refinement factor (>= 1)
     float slack;          // bound on |nominal cell boundary - true assignment boundary|
     int n[3];             // cells per axis
     uint32_t n_pts;
@@ -84,9 +87,11 @@ struct Grid {
     size_t n_cells = 0;
 };
 
-// Builds the grid over `xyz` (device, (n,3) dense).  `cell_edge` <= 0 picks the edge
-// from `target_occupancy` (mean points per cell of the bounding box).
-int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, cudaStream_t stream, Grid* out);
+// Builds the grid over `xyz` (device, (n,3) dense).  `cell_edge` <= 0 picks the (y, z) edge
+// from `target_occupancy` (mean points per h^3 of the bounding box).  Cells are `x_refine`
+// times finer along x (the contiguous axis), which costs nothing at query time: a query
+// still reads one contiguous span per (y, z) row, only trimmed more tightly.
+int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, int x_refine, cudaStream_t stream, Grid* out);
 
 // Sorts `query` (device, (nq,3)) by the cell of `grid` it falls in (clamped) and
 // returns float4 (x, y, z, bits(original index)) records in that order.

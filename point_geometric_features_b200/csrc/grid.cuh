@@ -16,7 +16,7 @@ __device__ __forceinline__ int cell_coord(float x, float lo, float inv_h, int n)
 
 __device__ __forceinline__ uint32_t cell_index(const GridView& g, float x, float y, float z)
 {
-    const int cx = cell_coord(x, g.lo[0], g.inv_h, g.n[0]);
+    const int cx = cell_coord(x, g.lo[0], g.inv_hx, g.n[0]);
     const int cy = cell_coord(y, g.lo[1], g.inv_h, g.n[1]);
     const int cz = cell_coord(z, g.lo[2], g.inv_h, g.n[2]);
     return ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0] + (uint32_t)cx;

@@ -191,7 +191,7 @@ static size_t max_cells_for(size_t n)
     return std::min<size_t>(cap, (size_t)1 << 28);
 }
 
-int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, cudaStream_t stream, Grid* out)
+int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, int x_refine, cudaStream_t stream, Grid* out)
 {
     if (n == 0 || n > 0xfffffff0ull) { set_error("grid_build: n=%zu out of range", n); return PGEOF_EINVAL; }
     KernelTimer timer("grid_build", stream);
@@ -224,17 +224,26 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
     // float32 cannot resolve cells much finer than an ulp of the coordinates
     h = std::max(h, std::max(maxabs * 1e-5, 1e-30));
     const size_t cap = max_cells_for(n);
+    int xf = std::max(1, std::min(x_refine, 16));
     int nc[3];
     for (;;) {
         double cells = 1;
-        for (int d = 0; d < 3; ++d) { const double c = std::floor(ext[d] / h) + 1; nc[d] = (int)std::min(c, 2e9); cells *= c; }
+        for (int d = 0; d < 3; ++d) {
+            const double edge = d == 0 ? h / xf : h;
+            const double c = std::floor(ext[d] / edge) + 1;
+            nc[d] = (int)std::min(c, 2e9);
+            cells *= c;
+        }
         if (cells <= (double)cap) break;
-        h *= 1.26;
+        if (xf > 1) xf >>= 1; else h *= 1.26;
     }
     GridView& g = out->view;
     for (int d = 0; d < 3; ++d) { g.lo[d] = lo[d]; g.n[d] = nc[d]; }
     g.h = (float)h;
     g.inv_h = 1.0f / g.h;
+    g.hx = (float)(h / xf);
+    g.inv_hx = 1.0f / g.hx;
+    g.xf = xf;
     g.slack = (float)((2.0 * maxabs + h) * 9.5367431640625e-7);   // 2^-20
     g.n_pts = (uint32_t)n;
     out->n_cells = (size_t)nc[0] * nc[1] * nc[2];

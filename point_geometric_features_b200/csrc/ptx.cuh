@@ -22,19 +22,23 @@ __device__ __forceinline__ void mbarrier_arrive_expect_tx(uint64_t* bar, uint32_
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ bool mbarrier_try_wait(uint64_t* bar, uint32_t parity)
 {
+    uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
         : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity)
+{
+    while (!mbarrier_try_wait(bar, parity)) {}
 }
 
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-B aligned; completes on `bar`

@@ -1,20 +1,35 @@
-// search.cu -- knn_search / radius_search on the uniform grid, one warp per query.
+// search.cu -- knn_search / radius_search on the uniform grid.
 // Replaces nanoflann_knn_search / nanoflann_radius_search (include/nn_search.hpp:31-132).
 //
-// Per query: (1) seed a radius from the local density of the 3x3x3 cell block,
-// (2) scan the cells that intersect the ball, keeping keys under the threshold in a
-// per-warp shared-memory buffer, (3) if the ball holds fewer than k points grow it, if it
-// overflows the buffer shrink / bisect the threshold, (4) pick the k smallest keys with a
-// register-resident counting bisection, (5) bitonic-sort them with warp shuffles and write
-// the row.  Exactness: a point is only ever rejected by the 64-bit key threshold, and the
-// cell coverage of a ball is computed with directed rounding (see search_core.cuh).
+// Two kernels share the grid and the exactness argument (a point is only ever rejected by the
+// 64-bit (d2, index) key threshold, and the cell coverage of a ball is computed with directed
+// rounding, see search_core.cuh):
+//
+//  * knn_tile_kernel (kNN, k <= 64): ONE THREAD PER QUERY, one warp per 32 consecutive queries of
+//    the cell-sorted order.  The 32 queries of a warp live in one (y, z) cell row, so they share one
+//    candidate region: the cells that intersect the warp's query bounding box dilated by the
+//    search radius R (R seeded from the local density).  Every candidate is loaded ONCE per warp
+//    (a warp-uniform 128-bit load) and tested by the 32 lanes against their own query -- no
+//    ballots, shuffles or partially filled 32-candidate chunks in the inner loop.  Survivors
+//    (d2 <= fl(0.9999 R^2)) are appended to a per-lane shared-memory list; a per-lane counting
+//    bisection trims the list to [k, NSORT] entries; the rows are then sorted and written.
+//    Lanes whose ball held fewer than k points, overflowed the list or hit an exact-distance tie at
+//    the trimming boundary are finished by the generic per-query routine inside the same kernel.
+//
+//  * search_kernel (kNN with 64 < k <= 512, radius modes): one warp per query.  Per query:
+//    (1) seed a radius from the local density of the 3x3x3 cell block, (2) scan the cells that
+//    intersect the ball, keeping keys under the threshold in a per-warp shared-memory buffer,
+//    (3) if the ball holds fewer than k points grow it, if it overflows the buffer shrink /
+//    bisect the threshold, (4) pick the k smallest keys with a register-resident counting
+//    bisection, (5) bitonic-sort them with warp shuffles and write the row.
 //
 // Roofline: algorithmic bytes/query = 12 (query) + 12 (data, once) + 8k (idx + d2) = 24 + 8k.
-// The kernel is issue bound (distance + compaction + sort), not HBM bound: DESIGN.md.
+// Both kernels are issue bound (distance + select + sort), not HBM bound: DESIGN.md.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
+#include "ptx.cuh"
 #include "search_core.cuh"
 
 namespace pgeof {
@@ -41,11 +56,107 @@ struct SearchArgs {
     uint32_t* nn_ptr;        // RADIUS_COUNT: per-row counts out; RADIUS_CSR: row offsets in
 };
 
+// ---------------------------------------------------------------------------------------
+// generic per-query kNN (one warp): collect the keys under an adaptive threshold
+// ---------------------------------------------------------------------------------------
+template <int CAP>
+__device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, float qy, float qz, uint32_t k, float target,
+                                                u64* keybuf, int lane, u64* tau_out)
+{
+    uint32_t n27, cells27;
+    block27_count(g, qx, qy, qz, lane, &n27, &cells27);
+    const float rho = fmaxf((float)n27, 1.f) / ((float)max(cells27, 1u) * g.hx * g.h * g.h);
+    float R = cbrtf(target / (4.18879f * rho)) + bbox_distance(g, qx, qy, qz);
+    float Rg = R, Rg_hi = 0.f;
+    u64 tau_lo = 0, tau_hi = 0;
+    bool have_lo = false, have_hi = false;
+    int shrinks = 0;
+    u64 tau = tau_from_radius(R);
+    uint32_t c = 0;
+    for (int it = 0; it < 512; ++it) {
+        c = scan_ball<CAP, true>(g, qx, qy, qz, Rg, tau, keybuf, lane);
+        if (c < k) {
+            tau_lo = tau; have_lo = true;
+            if (have_hi) { tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
+            else {
+                const float f = fminf(fmaxf(cbrtf(1.2f * target / fmaxf((float)c, 0.5f)), 1.2f), 2.5f);
+                R *= f; Rg = R; tau = tau_from_radius(R);
+            }
+        } else if (c > (uint32_t)CAP) {
+            tau_hi = tau; have_hi = true; Rg_hi = Rg;
+            // dense spot: shrink the ball by the density estimate (twice at most) ...
+            bool shrunk = false;
+            if (!have_lo && shrinks < 2) {
+                const float Rn = R * fminf(fmaxf(cbrtf(target / (float)c), 0.3f), 0.9f);
+                const u64 tn = tau_from_radius(Rn);
+                if (tn < tau_hi && (tn >> 32) != 0) { R = Rn; Rg = R; tau = tn; ++shrinks; shrunk = true; }
+            }
+            // ... else bisect the key space between tau_lo (0: nothing is below it) and tau_hi:
+            // always converges because keys are distinct (many duplicates / exact ties land here)
+            if (!shrunk) { have_lo = true; tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
+        } else break;
+    }
+    *tau_out = tau;
+    return c;
+}
+
+// keybuf[0, c) holds keys <= tau, c <= CAP: pick the `need` smallest and return them sorted in v
+// (element m * 32 + lane, padded with kKeyMax).
+template <int NSORT, int CAP>
+__device__ __forceinline__ void select_and_sort(u64* keybuf, uint32_t c, u64 tau, uint32_t need, int lane, u64 (&v)[NSORT / 32])
+{
+    constexpr int M = NSORT / 32, MC = CAP / 32;
+    if (c > (uint32_t)NSORT) {
+        u64 key[MC];
+#pragma unroll
+        for (int r = 0; r < MC; ++r) {
+            const uint32_t e = r * 32 + lane;
+            key[r] = ((uint32_t)(r * 32) < c && e < c) ? keybuf[e] : kKeyMax;
+        }
+        const u64 t = select_threshold<MC>(key, c, tau, need, NSORT);
+        __syncwarp();
+        const unsigned lt = lanemask_lt();
+        uint32_t off = 0;
+#pragma unroll
+        for (int r = 0; r < MC; ++r) {
+            if ((uint32_t)(r * 32) < c) {
+                const bool acc = key[r] <= t;
+                const unsigned m = __ballot_sync(kFull, acc);
+                if (acc) keybuf[off + __popc(m & lt)] = key[r];
+                off += __popc(m);
+            }
+        }
+        __syncwarp();
+        c = off;
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const uint32_t e = m * 32 + lane;
+        v[m] = e < c ? keybuf[e] : kKeyMax;
+    }
+    warp_bitonic_sort<M>(v, lane);
+}
+
+template <int M>
+__device__ __forceinline__ void write_knn_row(const SearchArgs& a, uint32_t row, uint32_t k, const u64 (&v)[M], int lane)
+{
+    uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)row * k;
+    float* d2 = a.sqr_dist + (size_t)row * k;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const uint32_t e = m * 32 + lane;
+        if (e < k) { idx[e] = key_idx(v[m]); d2[e] = key_d2(v[m]); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// one warp per query: kNN with k > 64 and the radius modes
+// ---------------------------------------------------------------------------------------
 template <int NSORT, int MODE>
 __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, const SearchArgs a)
 {
     using Cfg = SearchCfg<NSORT, MODE>;
-    constexpr int M = Cfg::M, CAP = Cfg::CAP, MC = Cfg::MC;
+    constexpr int M = Cfg::M, CAP = Cfg::CAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64* keybuf = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * CAP;
@@ -60,38 +171,7 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
     uint32_t c = 0;     // keys under `tau` (<= CAP once the loops below finish)
     u64 tau = 0;
     if (MODE == SEARCH_KNN) {
-        uint32_t n27, cells27;
-        block27_count(g, qx, qy, qz, lane, &n27, &cells27);
-        const float rho = fmaxf((float)n27, 1.f) / ((float)max(cells27, 1u) * g.h * g.h * g.h);
-        float R = cbrtf(a.target / (4.18879f * rho)) + bbox_distance(g, qx, qy, qz);
-        float Rg = R, Rg_hi = 0.f;
-        u64 tau_lo = 0, tau_hi = 0;
-        bool have_lo = false, have_hi = false;
-        int shrinks = 0;
-        tau = tau_from_radius(R);
-        for (int it = 0; it < 512; ++it) {
-            c = scan_ball<CAP, true>(g, qx, qy, qz, Rg, tau, keybuf, lane);
-            if (c < k) {
-                tau_lo = tau; have_lo = true;
-                if (have_hi) { tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
-                else {
-                    const float f = fminf(fmaxf(cbrtf(1.2f * a.target / fmaxf((float)c, 0.5f)), 1.2f), 2.5f);
-                    R *= f; Rg = R; tau = tau_from_radius(R);
-                }
-            } else if (c > (uint32_t)CAP) {
-                tau_hi = tau; have_hi = true; Rg_hi = Rg;
-                // dense spot: shrink the ball by the density estimate (twice at most) ...
-                bool shrunk = false;
-                if (!have_lo && shrinks < 2) {
-                    const float Rn = R * fminf(fmaxf(cbrtf(a.target / (float)c), 0.3f), 0.9f);
-                    const u64 tn = tau_from_radius(Rn);
-                    if (tn < tau_hi && (tn >> 32) != 0) { R = Rn; Rg = R; tau = tn; ++shrinks; shrunk = true; }
-                }
-                // ... else bisect the key space between tau_lo (0: nothing is below it) and tau_hi:
-                // always converges because keys are distinct (many duplicates / exact ties land here)
-                if (!shrunk) { have_lo = true; tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
-            } else break;
-        }
+        c = knn_collect<CAP>(g, qx, qy, qz, k, a.target, keybuf, lane, &tau);
     } else {
         const float r2 = __fmul_rn(a.radius, a.radius);                       // nn_search.hpp:98
         const uint32_t r2b = __float_as_uint(r2);
@@ -132,45 +212,11 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
     // ---- select the `need` smallest keys and sort them -------------------------------
     const uint32_t need = (MODE == SEARCH_KNN) ? k : min(c, k);
     u64 v[M];
-    if (c > (uint32_t)NSORT) {
-        u64 key[MC];
-#pragma unroll
-        for (int r = 0; r < MC; ++r) {
-            const uint32_t e = r * 32 + lane;
-            key[r] = ((uint32_t)(r * 32) < c && e < c) ? keybuf[e] : kKeyMax;
-        }
-        const u64 t = select_threshold<MC>(key, c, tau, need, NSORT);
-        __syncwarp();
-        const unsigned lt = lanemask_lt();
-        uint32_t off = 0;
-#pragma unroll
-        for (int r = 0; r < MC; ++r) {
-            if ((uint32_t)(r * 32) < c) {
-                const bool acc = key[r] <= t;
-                const unsigned m = __ballot_sync(kFull, acc);
-                if (acc) keybuf[off + __popc(m & lt)] = key[r];
-                off += __popc(m);
-            }
-        }
-        __syncwarp();
-        c = off;
-    }
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const uint32_t e = m * 32 + lane;
-        v[m] = e < c ? keybuf[e] : kKeyMax;
-    }
-    warp_bitonic_sort<M>(v, lane);
+    select_and_sort<NSORT, CAP>(keybuf, c, tau, need, lane, v);
 
     // ---- write the row ----------------------------------------------------------------
     if (MODE == SEARCH_KNN) {
-        uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)row * k;
-        float* d2 = a.sqr_dist + (size_t)row * k;
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const uint32_t e = m * 32 + lane;
-            if (e < k) { idx[e] = key_idx(v[m]); d2[e] = key_d2(v[m]); }
-        }
+        write_knn_row<M>(a, row, k, v, lane);
     } else if (MODE == SEARCH_RADIUS) {
         int32_t* idx = reinterpret_cast<int32_t*>(a.indices) + (size_t)row * k;
         float* d2 = a.sqr_dist + (size_t)row * k;
@@ -197,6 +243,287 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// one thread per query, one warp per 32 cell-sorted queries: kNN with k <= 64
+// ---------------------------------------------------------------------------------------
+template <int NSORT>
+struct TileCfg {
+    static constexpr int M = NSORT / 32;
+    static constexpr int LCAP = NSORT + 24;        // survivors a lane can hold
+    static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
+    static constexpr int WARPS = 2;
+    static constexpr int CMAX = 960;               // candidates staged per pass (16 B each)
+    static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
+    static constexpr int STAGE_BYTES = CMAX * 16;
+    static constexpr int BAR_BYTES = 16;
+    static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
+    static constexpr int GEN_CAP = 256;            // key buffer of the generic fallback (aliases the staging area)
+    static_assert(STAGE_BYTES >= GEN_CAP * 8, "fallback key buffer must fit the staging area");
+    static_assert(LIST_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "alignment");
+    static constexpr int MAX_PASSES = 4;           // (y, z) rows one warp may straddle before it falls back
+    // a list entry is (bits(d2) & ~SLOT_MASK) | staged slot: 21 bits of distance order the trimming,
+    // the slot finds the candidate again when the exact key is rebuilt for the sort
+    static constexpr uint32_t SLOT_BITS = 11;
+    static constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1;
+    static_assert(CMAX <= (1 << SLOT_BITS), "slot field too small");
+    static_assert(NSORT * STRIDE * 4 <= LIST_BYTES && NSORT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
+};
+
+// order preserving float <-> uint maps (for REDUX min / max)
+__device__ __forceinline__ uint32_t f2o(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
+__device__ __forceinline__ float o2f(uint32_t o) { return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu)); }
+
+template <int NSORT>
+__global__ void __launch_bounds__(TileCfg<NSORT>::WARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
+{
+    using Cfg = TileCfg<NSORT>;
+    constexpr int M = Cfg::M, LCAP = Cfg::LCAP, S = Cfg::STRIDE;
+    extern __shared__ __align__(128) unsigned char smem_tile[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wsm = smem_tile + (size_t)warp * Cfg::SMEM_WARP_BYTES;
+    float4* stage = reinterpret_cast<float4*>(wsm);
+    uint32_t* list = reinterpret_cast<uint32_t*>(wsm + Cfg::STAGE_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + Cfg::STAGE_BYTES + Cfg::LIST_BYTES);
+    const uint32_t base = (blockIdx.x * Cfg::WARPS + warp) * 32u;
+    if (base >= a.n_query) return;
+    const uint32_t k = a.k;
+    if (lane == 0) { ptx::mbarrier_init(bar, 1); ptx::fence_mbarrier_init(); }
+    __syncwarp();
+    uint32_t parity = 0;
+
+    const bool valid = base + lane < a.n_query;
+    const float4 q4 = valid ? __ldg(a.queries + base + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    const uint32_t row = __float_as_uint(q4.w);
+    const int cqx = cell_coord(qx, g.lo[0], g.inv_hx, g.n[0]);
+    const int cqy = cell_coord(qy, g.lo[1], g.inv_h, g.n[1]);
+    const int cqz = cell_coord(qz, g.lo[2], g.inv_h, g.n[2]);
+    const uint32_t rowid = (uint32_t)cqz * (uint32_t)g.n[1] + (uint32_t)cqy;
+
+    unsigned remaining = __ballot_sync(kFull, valid);
+    unsigned slow = 0;                       // lanes finished by the generic routine
+    for (int pass = 0; remaining; ++pass) {
+        // ---- the lanes of this pass: queries in the (y, z) cell row of the first remaining lane ----
+        const int leader = __ffs(remaining) - 1;
+        const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
+        const unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow);
+        remaining &= ~active;
+        if (pass >= Cfg::MAX_PASSES) { slow |= active; continue; }
+        const bool mine = (active >> lane) & 1u;
+
+        // ---- bounding box of the active queries -----------------------------------------------
+        const float xmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qx) : 0xffffffffu));
+        const float xmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qx) : 0u));
+        const float ymin = o2f(__reduce_min_sync(kFull, mine ? f2o(qy) : 0xffffffffu));
+        const float ymax = o2f(__reduce_max_sync(kFull, mine ? f2o(qy) : 0u));
+        const float zmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qz) : 0xffffffffu));
+        const float zmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qz) : 0u));
+        const int cxa = __reduce_min_sync(kFull, mine ? cqx : 0x7fffffff);
+        const int cxb = __reduce_max_sync(kFull, mine ? cqx : -1);
+        const int cy = __shfl_sync(kFull, cqy, leader), cz = __shfl_sync(kFull, cqz, leader);
+
+        // ---- density of the block around them -> search radius R ------------------------------
+        float R;
+        {
+            const int bx0 = max(cxa - g.xf, 0), bx1 = min(cxb + g.xf, g.n[0] - 1);
+            int c = 0, nc = 0;
+            if (lane < 9) {
+                const int by = cy + lane % 3 - 1, bz = cz + lane / 3 - 1;
+                if (by >= 0 && by < g.n[1] && bz >= 0 && bz < g.n[2]) {
+                    const uint32_t rb = ((uint32_t)bz * (uint32_t)g.n[1] + (uint32_t)by) * (uint32_t)g.n[0];
+                    c = (int)(__ldg(g.cell_start + rb + bx1 + 1) - __ldg(g.cell_start + rb + bx0));
+                    nc = bx1 - bx0 + 1;
+                }
+            }
+            c = __reduce_add_sync(kFull, c);
+            nc = __reduce_add_sync(kFull, nc);
+            const float rho = fmaxf((float)c, 1.f) / ((float)max(nc, 1) * g.hx * g.h * g.h);
+            R = cbrtf(a.target / (4.18879f * rho));
+        }
+
+        // ---- candidate region: cells meeting the dilated box; one contiguous span per (y, z) row ---
+        const int cx0 = cell_coord(__fsub_rd(xmin, R), g.lo[0], g.inv_hx, g.n[0]);
+        const int cx1 = cell_coord(__fadd_ru(xmax, R), g.lo[0], g.inv_hx, g.n[0]);
+        const int cy0 = cell_coord(__fsub_rd(ymin, R), g.lo[1], g.inv_h, g.n[1]);
+        const int cy1 = cell_coord(__fadd_ru(ymax, R), g.lo[1], g.inv_h, g.n[1]);
+        const int cz0 = cell_coord(__fsub_rd(zmin, R), g.lo[2], g.inv_h, g.n[2]);
+        const int cz1 = cell_coord(__fadd_ru(zmax, R), g.lo[2], g.inv_h, g.n[2]);
+        const uint32_t nyr = (uint32_t)(cy1 - cy0 + 1);
+        const uint32_t nrows = nyr * (uint32_t)(cz1 - cz0 + 1);
+        if (nrows > 32u) { slow |= active; continue; }
+        uint32_t s = 0, len = 0;
+        if ((uint32_t)lane < nrows) {
+            const int rz = cz0 + (int)((uint32_t)lane / nyr), ry = cy0 + (int)((uint32_t)lane % nyr);
+            const uint32_t rb = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
+            s = __ldg(g.cell_start + rb + cx0);
+            len = __ldg(g.cell_start + rb + cx1 + 1) - s;
+        }
+        // exclusive prefix of the span lengths = where each row lands in the staging area
+        uint32_t off = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFull, off, o);
+            if (lane >= o) off += t;
+        }
+        const uint32_t C = __shfl_sync(kFull, off, 31);
+        off -= len;
+        if (C > (uint32_t)Cfg::CMAX) { slow |= active; continue; }   // dense spot: the generic routine adapts its ball
+
+        // ---- stage the region: one 1-D TMA bulk copy per row, all rows in flight at once ---------
+        __syncwarp();
+        if (lane == 0) { ptx::fence_proxy_async_smem(); ptx::mbarrier_arrive_expect_tx(bar, C * 16u); }
+        __syncwarp();
+        if (len) ptx::bulk_g2s(stage + off, g.pts + s, len * 16u, bar);
+        ptx::mbarrier_wait(bar, parity);
+        parity ^= 1u;
+
+        // ---- scan: every candidate is read once per warp (broadcast) and tested by all lanes ------
+        // accept iff d2 <= t2 with t2 strictly inside R^2, so every accepted point is in the region
+        const float t2 = mine ? __fmul_rd(__fmul_rd(R, R), 0.9999f) : -1.f;
+        uint32_t* const wbase = list + lane;
+        // shared-memory byte address of the lane's next free entry: advances by one stride per
+        // survivor, also past the end (the store is then suppressed, the count stays exact)
+        const uint32_t waddr0 = ptx::smem_addr(wbase);
+        const uint32_t wend = waddr0 + LCAP * S * 4;
+        uint32_t waddr = waddr0;
+        // branch-free append (the compiler turns the equivalent C++ into a divergent branch per candidate)
+#define PGEOF_TILE_APPEND(D2, SLOT)                                                           \
+        asm volatile("{\n\t.reg .pred p, q;\n\t"                                              \
+                     "setp.le.f32 p, %1, %2;\n\t"                                             \
+                     "setp.lt.and.u32 q, %0, %3, p;\n\t"                                      \
+                     "@q st.shared.u32 [%0], %4;\n\t"                                         \
+                     "@p add.u32 %0, %0, %5;\n\t}"                                            \
+                     : "+r"(waddr)                                                            \
+                     : "f"(D2), "f"(t2), "r"(wend), "r"((__float_as_uint(D2) & ~Cfg::SLOT_MASK) | (SLOT)), "n"(S * 4));
+        {
+            uint32_t c = 0;
+            for (; c + 8 <= C; c += 8) {
+                float d[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float4 p = stage[c + i]; d[i] = sqdist_f32(qx, qy, qz, p.x, p.y, p.z); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) PGEOF_TILE_APPEND(d[i], c + i)
+            }
+            for (; c < C; ++c) {
+                const float4 p = stage[c];
+                const float d = sqdist_f32(qx, qy, qz, p.x, p.y, p.z);
+                PGEOF_TILE_APPEND(d, c)
+            }
+        }
+#undef PGEOF_TILE_APPEND
+        __syncwarp();
+        const uint32_t cnt = (waddr - waddr0) / (S * 4);
+        bool ok = mine && cnt >= k && cnt <= (uint32_t)LCAP;
+        __syncwarp();
+
+        // ---- trim the list to [k, NSORT] entries: per-lane counting bisection on the entry word ----
+        // (entries order by their top 21 bits = truncated d2; everything sharing a truncated value is
+        // kept or dropped together, so the kept set is always a prefix of the true (d2, index) order)
+        uint32_t m = cnt;
+        bool pending = ok && cnt > (uint32_t)NSORT;
+        if (__any_sync(kFull, pending)) {
+            const uint32_t maxcnt = __reduce_max_sync(kFull, pending ? cnt : 0u);
+            // thresholds u: keep an entry iff (entry >> SLOT_BITS) < u
+            uint32_t lo = 0, hi = (__float_as_uint(t2) >> Cfg::SLOT_BITS) + 1u, thr = hi;
+            float cur_cnt = (float)cnt, cur_d2 = t2;
+            const float want = 0.5f * (float)(k + NSORT);
+            for (int it = 0; it < 28 && __any_sync(kFull, pending); ++it) {
+                uint32_t mid = lo + (hi - lo) / 2;
+                if (it < 4) {
+                    const float gd2 = cur_d2 * exp2f(0.6666667f * log2f(want / cur_cnt));
+                    const uint32_t guess = (__float_as_uint(gd2) >> Cfg::SLOT_BITS) + 1u;
+                    if (guess > lo && guess < hi) mid = guess;
+                }
+                const uint32_t cut_word = mid << Cfg::SLOT_BITS;
+                uint32_t n = 0;
+#pragma unroll 8
+                for (uint32_t i = 0; i < maxcnt; ++i) n += (i < cnt && wbase[i * S] < cut_word) ? 1u : 0u;
+                if (pending) {
+                    if (n < k) lo = mid;
+                    else if (n > (uint32_t)NSORT) hi = mid;
+                    else { thr = mid; m = n; pending = false; }
+                    cur_cnt = fmaxf((float)n, 0.5f);
+                    cur_d2 = __uint_as_float((mid << Cfg::SLOT_BITS) - 1u);
+                    if (pending && hi - lo <= 1u) { pending = false; ok = false; }   // too many (near-)ties at the window
+                }
+            }
+            if (pending) { pending = false; ok = false; }
+            // compact the kept entries to the front of the list (in place: writes trail reads)
+            const bool cut = ok && m < cnt;
+            if (__any_sync(kFull, cut)) {
+                const uint32_t cut_word = thr << Cfg::SLOT_BITS;
+                uint32_t pos = 0;
+#pragma unroll 4
+                for (uint32_t i = 0; i < maxcnt; ++i) {
+                    if (cut && i < cnt) {
+                        const uint32_t w = wbase[i * S];
+                        if (w < cut_word) { wbase[pos * S] = w; ++pos; }
+                    }
+                }
+            }
+        }
+        slow |= __ballot_sync(kFull, mine && !ok);
+        __syncwarp();
+
+        // ---- rebuild the exact keys and sort them: one thread per row, all in registers ---------
+        {
+            u64 v[NSORT];
+#pragma unroll
+            for (int i = 0; i < NSORT; ++i) {
+                const bool live = ok && (uint32_t)i < m;
+                const uint32_t slot = live ? (wbase[i * S] & Cfg::SLOT_MASK) : 0u;
+                const float4 p = stage[slot];
+                v[i] = live ? make_key(sqdist_f32(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w)) : kKeyMax;
+            }
+            RegOddEvenSort<NSORT, 0, NSORT>::run(v);
+            // transpose through shared memory (the staged candidates and the lists are dead now):
+            // plane[i * S + lane] = i-th neighbour of this lane's row
+            __syncwarp();
+            uint32_t* plane_d = list + lane;
+            uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
+#pragma unroll
+            for (int i = 0; i < NSORT; ++i) {
+                if ((uint32_t)i < k) { plane_d[i * S] = (uint32_t)(v[i] >> 32); plane_i[i * S] = (uint32_t)v[i]; }
+            }
+        }
+        __syncwarp();
+        // ---- write the finished rows, one coalesced row at a time ---------------------------------
+        {
+            const uint32_t* plane_d = list;
+            const uint32_t* plane_i = reinterpret_cast<const uint32_t*>(stage);
+            unsigned okm = __ballot_sync(kFull, ok);
+            while (okm) {
+                const int q = __ffs(okm) - 1;
+                okm &= okm - 1;
+                const uint32_t rowq = __shfl_sync(kFull, row, q);
+                uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)rowq * k;
+                float* d2 = a.sqr_dist + (size_t)rowq * k;
+#pragma unroll
+                for (int r = 0; r < M; ++r) {
+                    const uint32_t e = r * 32 + lane;
+                    if (e < k) { idx[e] = plane_i[e * S + q]; d2[e] = __uint_as_float(plane_d[e * S + q]); }
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- generic per-query routine for the lanes the tile path could not finish ----------------
+    u64* keybuf = reinterpret_cast<u64*>(stage);
+    while (slow) {
+        const int q = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const float sx = __shfl_sync(kFull, qx, q), sy = __shfl_sync(kFull, qy, q), sz = __shfl_sync(kFull, qz, q);
+        const uint32_t rowq = __shfl_sync(kFull, row, q);
+        u64 tau;
+        const uint32_t c = knn_collect<Cfg::GEN_CAP>(g, sx, sy, sz, k, a.target, keybuf, lane, &tau);
+        u64 v[M];
+        select_and_sort<NSORT, Cfg::GEN_CAP>(keybuf, c, tau, k, lane, v);
+        write_knn_row<M>(a, rowq, k, v, lane);
+        __syncwarp();
+    }
+}
+
 template <int NSORT, int MODE>
 int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
@@ -208,6 +535,22 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     {
         KernelTimer timer(MODE == SEARCH_KNN ? "knn_search" : "radius_search", stream);
         kern<<<blocks, kWarps * 32, smem, stream>>>(g, a);
+    }
+    PGEOF_LAUNCH_CHECK();
+    return PGEOF_OK;
+}
+
+template <int NSORT>
+int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
+{
+    using Cfg = TileCfg<NSORT>;
+    const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
+    auto kern = knn_tile_kernel<NSORT>;
+    PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
+    {
+        KernelTimer timer("knn_search", stream);
+        kern<<<blocks, Cfg::WARPS * 32, smem, stream>>>(g, a);
     }
     PGEOF_LAUNCH_CHECK();
     return PGEOF_OK;
@@ -240,21 +583,24 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     if (n_query > 0xfffffff0ull) { set_error("n_query too large"); return PGEOF_EINVAL; }
     Grid grid;
     float target = 0.f;
+    const bool tile = mode == SEARCH_KNN && k <= 64 && env_float("PGEOF_KNN_TILE", 1.f) != 0.f;
     if (mode == SEARCH_KNN) {
-        // ball seeded to hold k + 2 sigma + 2 points; cell edge ~ that ball's radius
-        target = (float)k + 2.f * std::sqrt((float)k) + 2.f;
-        const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", 0.25f));
-        PGEOF_TRY(grid_build(data, n_data, 0.f, occ, stream, &grid));
+        // ball seeded to hold k + 2..2.5 sigma + 2 points.  Tile path: cell edge h slightly above that
+        // ball's radius so that a warp's region is 3 x 3 (y, z) rows, cells 4x finer along x.
+        target = (float)k + (tile ? 2.5f : 2.f) * std::sqrt((float)k) + 2.f;
+        const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", tile ? 0.33f : 0.25f));
+        PGEOF_TRY(grid_build(data, n_data, 0.f, occ, tile ? (int)env_float("PGEOF_KNN_XF", 4.f) : 1, stream, &grid));
     } else {
         if (!(radius >= 0.f) || !std::isfinite(radius)) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
         const float edge = radius * env_float("PGEOF_RADIUS_CELL_SCALE", 1.0f);
-        PGEOF_TRY(grid_build(data, n_data, edge > 0.f ? edge : 1.f, 0.f, stream, &grid));
+        PGEOF_TRY(grid_build(data, n_data, edge > 0.f ? edge : 1.f, 0.f, 1, stream, &grid));
     }
     DeviceBuffer qsorted;
     const float4* qrec;
     if (query == data && n_query == n_data) qrec = grid.view.pts;   // self query: reuse the sorted cloud
     else { PGEOF_TRY(grid_sort_queries(grid, query, n_query, stream, &qsorted)); qrec = qsorted.as<float4>(); }
     SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr};
+    if (tile) return k <= 32 ? launch_tile<32>(grid.view, a, stream) : launch_tile<64>(grid.view, a, stream);
     switch (mode) {
         case SEARCH_KNN: return dispatch_search<SEARCH_KNN>(k, grid.view, a, stream);
         case SEARCH_RADIUS: return dispatch_search<SEARCH_RADIUS>(k, grid.view, a, stream);

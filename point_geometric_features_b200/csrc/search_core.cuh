@@ -55,8 +55,8 @@ template <int CAP, bool STORE>
 __device__ __forceinline__ uint32_t scan_ball(const GridView& g, float qx, float qy, float qz, float R, u64 tau,
                                               u64* __restrict__ keybuf, int lane)
 {
-    const int cx0 = cell_coord(__fsub_rd(qx, R), g.lo[0], g.inv_h, g.n[0]);
-    const int cx1 = cell_coord(__fadd_ru(qx, R), g.lo[0], g.inv_h, g.n[0]);
+    const int cx0 = cell_coord(__fsub_rd(qx, R), g.lo[0], g.inv_hx, g.n[0]);
+    const int cx1 = cell_coord(__fadd_ru(qx, R), g.lo[0], g.inv_hx, g.n[0]);
     const int cy0 = cell_coord(__fsub_rd(qy, R), g.lo[1], g.inv_h, g.n[1]);
     const int cy1 = cell_coord(__fadd_ru(qy, R), g.lo[1], g.inv_h, g.n[1]);
     const int cz0 = cell_coord(__fsub_rd(qz, R), g.lo[2], g.inv_h, g.n[2]);
@@ -79,8 +79,8 @@ __device__ __forceinline__ uint32_t scan_ball(const GridView& g, float qx, float
             const float rem = __fsub_ru(__fsub_ru(R2u, __fmul_rd(gy, gy)), __fmul_rd(gz, gz));
             if (rem >= 0.f) {
                 const float xr = __fsqrt_ru(rem);
-                const int x0 = max(cx0, cell_coord(__fsub_rd(qx, xr), g.lo[0], g.inv_h, g.n[0]));
-                const int x1 = min(cx1, cell_coord(__fadd_ru(qx, xr), g.lo[0], g.inv_h, g.n[0]));
+                const int x0 = max(cx0, cell_coord(__fsub_rd(qx, xr), g.lo[0], g.inv_hx, g.n[0]));
+                const int x1 = min(cx1, cell_coord(__fadd_ru(qx, xr), g.lo[0], g.inv_hx, g.n[0]));
                 const uint32_t row = ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0];
                 s = __ldg(g.cell_start + row + x0);
                 e = __ldg(g.cell_start + row + x1 + 1);
@@ -117,10 +117,10 @@ __device__ __forceinline__ uint32_t scan_ball(const GridView& g, float qx, float
 // density estimate that seeds the search radius.
 __device__ __forceinline__ void block27_count(const GridView& g, float qx, float qy, float qz, int lane, uint32_t* pts, uint32_t* cells)
 {
-    const int cqx = cell_coord(qx, g.lo[0], g.inv_h, g.n[0]);
+    const int cqx = cell_coord(qx, g.lo[0], g.inv_hx, g.n[0]);
     const int cqy = cell_coord(qy, g.lo[1], g.inv_h, g.n[1]);
     const int cqz = cell_coord(qz, g.lo[2], g.inv_h, g.n[2]);
-    const int bx0 = max(cqx - 1, 0), bx1 = min(cqx + 1, g.n[0] - 1);
+    const int bx0 = max(cqx - g.xf, 0), bx1 = min(cqx + g.xf, g.n[0] - 1);
     uint32_t c = 0, nc = 0;
     if (lane < 9) {
         const int cy = cqy + lane % 3 - 1, cz = cqz + lane / 3 - 1;
@@ -146,7 +146,7 @@ __device__ __forceinline__ float bbox_distance(const GridView& g, float qx, floa
     float s = 0.f;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const float hi = fmaf((float)g.n[d], g.h, g.lo[d]);
+        const float hi = fmaf((float)g.n[d], d == 0 ? g.hx : g.h, g.lo[d]);
         const float gap = fmaxf(fmaxf(g.lo[d] - q[d], q[d] - hi), 0.f);
         s += gap * gap;
     }
@@ -224,5 +224,46 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&v)[M], int lane)
         }
     }
 }
+
+// Thread-local Batcher odd-even merge sort of N keys held in registers (N a power of two).
+// Every index is a compile-time constant after unrolling, so v[] never leaves the register
+// file; a compare-exchange is 2 ISETP + 4 SEL with no shuffles, and the 32 lanes of a warp sort
+// 32 independent lists at once (N = 64: 543 compare-exchanges).
+template <int N>
+__device__ __forceinline__ void reg_cmpswap(u64 (&v)[N], int i, int j)
+{
+    const u64 a = v[i], b = v[j];
+    const bool sw = a > b;
+    v[i] = sw ? b : a;
+    v[j] = sw ? a : b;
+}
+
+template <int N, int LO, int CNT, int R>
+struct RegOddEvenMerge {
+    static __device__ __forceinline__ void run(u64 (&v)[N])
+    {
+        constexpr int STEP = R * 2;
+        if constexpr (STEP < CNT) {
+            RegOddEvenMerge<N, LO, CNT, STEP>::run(v);
+            RegOddEvenMerge<N, LO + R, CNT, STEP>::run(v);
+#pragma unroll
+            for (int i = LO + R; i + R < LO + CNT; i += STEP) reg_cmpswap<N>(v, i, i + R);
+        } else {
+            reg_cmpswap<N>(v, LO, LO + R);
+        }
+    }
+};
+
+template <int N, int LO, int CNT>
+struct RegOddEvenSort {
+    static __device__ __forceinline__ void run(u64 (&v)[N])
+    {
+        if constexpr (CNT > 1) {
+            RegOddEvenSort<N, LO, CNT / 2>::run(v);
+            RegOddEvenSort<N, LO + CNT / 2, CNT / 2>::run(v);
+            RegOddEvenMerge<N, LO, CNT, 1>::run(v);
+        }
+    }
+};
 
 }  // namespace pgeof

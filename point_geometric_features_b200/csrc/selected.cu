@@ -76,8 +76,8 @@ template <typename T, bool ACC>
 __device__ __forceinline__ uint32_t sel_scan(const GridView& g, const T* __restrict__ xyz, float qfx, float qfy, float qfz, T qx, T qy,
                                              T qz, float Rg, Thr<T> thr, Mom<T>* mom, int lane)
 {
-    const int cx0 = cell_coord(__fsub_rd(qfx, Rg), g.lo[0], g.inv_h, g.n[0]);
-    const int cx1 = cell_coord(__fadd_ru(qfx, Rg), g.lo[0], g.inv_h, g.n[0]);
+    const int cx0 = cell_coord(__fsub_rd(qfx, Rg), g.lo[0], g.inv_hx, g.n[0]);
+    const int cx1 = cell_coord(__fadd_ru(qfx, Rg), g.lo[0], g.inv_hx, g.n[0]);
     const int cy0 = cell_coord(__fsub_rd(qfy, Rg), g.lo[1], g.inv_h, g.n[1]);
     const int cy1 = cell_coord(__fadd_ru(qfy, Rg), g.lo[1], g.inv_h, g.n[1]);
     const int cz0 = cell_coord(__fsub_rd(qfz, Rg), g.lo[2], g.inv_h, g.n[2]);
@@ -98,8 +98,8 @@ __device__ __forceinline__ uint32_t sel_scan(const GridView& g, const T* __restr
             const float rem = __fsub_ru(__fsub_ru(R2u, __fmul_rd(gy, gy)), __fmul_rd(gz, gz));
             if (rem >= 0.f) {
                 const float xr = __fsqrt_ru(rem);
-                const int x0 = max(cx0, cell_coord(__fsub_rd(qfx, xr), g.lo[0], g.inv_h, g.n[0]));
-                const int x1 = min(cx1, cell_coord(__fadd_ru(qfx, xr), g.lo[0], g.inv_h, g.n[0]));
+                const int x0 = max(cx0, cell_coord(__fsub_rd(qfx, xr), g.lo[0], g.inv_hx, g.n[0]));
+                const int x1 = min(cx1, cell_coord(__fadd_ru(qfx, xr), g.lo[0], g.inv_hx, g.n[0]));
                 const uint32_t row = ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0];
                 s = __ldg(g.cell_start + row + x0);
                 e = __ldg(g.cell_start + row + x1 + 1);
@@ -233,7 +233,7 @@ int selected_run(const T* xyz, const float* xyz_f32, size_t n, T radius, uint32_
     if (eig_order != PGEOF_EIG_LITERAL && eig_order != PGEOF_EIG_DOCUMENTED) { set_error("bad eig_order %d", eig_order); return PGEOF_EINVAL; }
     Grid grid;
     const float edge = (float)radius > 0.f ? (float)radius : 1.f;
-    PGEOF_TRY(grid_build(xyz_f32, n, edge, 0.f, stream, &grid));
+    PGEOF_TRY(grid_build(xyz_f32, n, edge, 0.f, 1, stream, &grid));
     DeviceBuffer ids;
     PGEOF_TRY(ids.alloc(n_ids * sizeof(int32_t), stream));
     PGEOF_CUDA(cudaMemcpyAsync(ids.ptr, ids_host, n_ids * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
