@@ -8,13 +8,18 @@
 //  * knn_tile_kernel (kNN, k <= 64): ONE THREAD PER QUERY, one warp per 32 consecutive queries of
 //    the cell-sorted order.  The 32 queries of a warp live in one (y, z) cell row, so they share one
 //    candidate region: the cells that intersect the warp's query bounding box dilated by the
-//    search radius R (R seeded from the local density).  Every candidate is loaded ONCE per warp
-//    (a warp-uniform 128-bit load) and tested by the 32 lanes against their own query -- no
-//    ballots, shuffles or partially filled 32-candidate chunks in the inner loop.  Survivors
-//    (d2 <= fl(0.9999 R^2)) are appended to a per-lane shared-memory list; a per-lane counting
-//    bisection trims the list to [k, NSORT] entries; the rows are then sorted and written.
-//    Lanes whose ball held fewer than k points, overflowed the list or hit an exact-distance tie at
-//    the trimming boundary are finished by the generic per-query routine inside the same kernel.
+//    search radius R (R seeded from the local density), staged in shared memory by one 1-D TMA
+//    bulk copy per cell row.  Every candidate is read ONCE per warp (a warp-uniform 128-bit
+//    load) and tested by the 32 lanes against their own query -- no ballots, shuffles or partially
+//    filled 32-candidate chunks in the inner loop.  Survivors (d2 <= fl(0.9999 R^2)) are appended
+//    to a per-lane shared-memory list as 32-bit words (22 bits of d2 | staged slot).  Each lane
+//    then loads its list into registers and runs a min/max sorting network that leaves the 64
+//    smallest of up to 96 (128) words in order; the exact (d2, index) pairs are rebuilt from the
+//    staged candidates in that order, rows whose truncated keys collided are repaired by an
+//    insertion sort on the exact order, and the rows are written coalesced through a
+//    shared-memory transpose.  Lanes whose ball held fewer than k points, overflowed the network
+//    or hit a truncated-distance tie between the k-th neighbour and a dropped key are finished by
+//    the generic per-query routine inside the same kernel.
 //
 //  * search_kernel (kNN with 64 < k <= 512, radius modes): one warp per query.  Per query:
 //    (1) seed a radius from the local density of the 3x3x3 cell block, (2) scan the cells that
@@ -54,7 +59,11 @@ struct SearchArgs {
     void* indices;           // uint32 (knn) / int32 (radius) dense rows, or CSR nn
     float* sqr_dist;
     uint32_t* nn_ptr;        // RADIUS_COUNT: per-row counts out; RADIUS_CSR: row offsets in
+    unsigned long long* stats;   // optional tile-kernel counters (PGEOF_KNN_STATS=1), else null
 };
+
+// tile-kernel counters: why queries left the fast path, and how much work the fast path did
+enum { ST_SHORT = 0, ST_OVER, ST_TIE, ST_REGION, ST_FIXED, ST_PASSES, ST_CANDS, ST_SURV, ST_N };
 
 // ---------------------------------------------------------------------------------------
 // generic per-query kNN (one warp): collect the keys under an adaptive threshold
@@ -246,38 +255,62 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
 // ---------------------------------------------------------------------------------------
 // one thread per query, one warp per 32 cell-sorted queries: kNN with k <= 64
 // ---------------------------------------------------------------------------------------
-template <int NSORT>
+// NOUT = sorted outputs kept per query (>= k), NEXTRA = further survivors the network can absorb.
+template <int NOUT, int NEXTRA>
 struct TileCfg {
-    static constexpr int M = NSORT / 32;
-    static constexpr int LCAP = NSORT + 24;        // survivors a lane can hold
+    static constexpr int NLOAD = NOUT + NEXTRA;    // survivors a lane can sort
+    static constexpr int SINK = 11;                // a batch of 8 appends may run 8 entries past the clamp (11: 16-B multiple)
+    static constexpr int LCAP = NLOAD + 1 + SINK;  // list entries per lane
     static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
     static constexpr int WARPS = 2;
-    static constexpr int CMAX = 960;               // candidates staged per pass (16 B each)
+    static constexpr int CMAX = NLOAD <= 96 ? 896 : 832;   // candidates staged per pass (16 B each), multiple of 8
     static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
     static constexpr int STAGE_BYTES = CMAX * 16;
     static constexpr int BAR_BYTES = 16;
     static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
     static constexpr int GEN_CAP = 256;            // key buffer of the generic fallback (aliases the staging area)
+    static constexpr int MAX_PASSES = 4;           // (y, z) rows one warp may straddle before it falls back
+    // a list entry / sort key is (bits(d2) & ~SLOT_MASK) | staged slot: 22 bits of distance order the
+    // network, the slot finds the candidate again when the exact (d2, index) pair is rebuilt
+    static constexpr uint32_t SLOT_BITS = 10;
+    static constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1;
+    static_assert(CMAX % 8 == 0 && CMAX <= (1 << SLOT_BITS), "slot field too small");
     static_assert(STAGE_BYTES >= GEN_CAP * 8, "fallback key buffer must fit the staging area");
     static_assert(LIST_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "alignment");
-    static constexpr int MAX_PASSES = 4;           // (y, z) rows one warp may straddle before it falls back
-    // a list entry is (bits(d2) & ~SLOT_MASK) | staged slot: 21 bits of distance order the trimming,
-    // the slot finds the candidate again when the exact key is rebuilt for the sort
-    static constexpr uint32_t SLOT_BITS = 11;
-    static constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1;
-    static_assert(CMAX <= (1 << SLOT_BITS), "slot field too small");
-    static_assert(NSORT * STRIDE * 4 <= LIST_BYTES && NSORT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
+    static_assert(NOUT * STRIDE * 4 <= LIST_BYTES && NOUT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
+    static_assert((1 << SLOT_BITS) * 16 <= SMEM_WARP_BYTES, "a padded slot must stay inside the warp's shared memory");
+    static_assert(NOUT % 32 == 0 && NEXTRA % 32 == 0 && NEXTRA <= NOUT, "network shape");
 };
 
 // order preserving float <-> uint maps (for REDUX min / max)
 __device__ __forceinline__ uint32_t f2o(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u); }
 __device__ __forceinline__ float o2f(uint32_t o) { return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu)); }
 
-template <int NSORT>
-__global__ void __launch_bounds__(TileCfg<NSORT>::WARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
+// Sorts the NLOAD keys of v and leaves the NOUT smallest, ascending, in v[0, NOUT).  Returns the
+// smallest key that was dropped (0xffffffff if none): 32-key blocks by odd-even merge sort, blocks
+// merged pairwise, then one half-cleaner against the (reversed) extra run and a bitonic merge.
+template <int NOUT, int NEXTRA>
+__device__ __forceinline__ uint32_t select_sort_network(uint32_t (&v)[NOUT + NEXTRA])
 {
-    using Cfg = TileCfg<NSORT>;
-    constexpr int M = Cfg::M, LCAP = Cfg::LCAP, S = Cfg::STRIDE;
+    constexpr int N = NOUT + NEXTRA;
+    RegOddEvenSort<N, 0, NOUT>::run(v);
+    RegOddEvenSort<N, NOUT, NEXTRA>::run(v);
+    uint32_t dropped = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < NEXTRA; ++i) {
+        const uint32_t a = v[NOUT - 1 - i], b = v[NOUT + i];
+        v[NOUT - 1 - i] = min(a, b);
+        dropped = min(dropped, max(a, b));
+    }
+    RegBitonicMerge<N, 0, NOUT>::run(v);
+    return dropped;
+}
+
+template <int NOUT, int NEXTRA>
+__global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
+{
+    using Cfg = TileCfg<NOUT, NEXTRA>;
+    constexpr int M = NOUT / 32, NLOAD = Cfg::NLOAD, S = Cfg::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_tile[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem_tile + (size_t)warp * Cfg::SMEM_WARP_BYTES;
@@ -308,7 +341,11 @@ __global__ void __launch_bounds__(TileCfg<NSORT>::WARPS * 32) knn_tile_kernel(co
         const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
         const unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow);
         remaining &= ~active;
-        if (pass >= Cfg::MAX_PASSES) { slow |= active; continue; }
+        if (pass >= Cfg::MAX_PASSES) {
+            slow |= active;
+            if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
+            continue;
+        }
         const bool mine = (active >> lane) & 1u;
 
         // ---- bounding box of the active queries -----------------------------------------------
@@ -350,7 +387,11 @@ __global__ void __launch_bounds__(TileCfg<NSORT>::WARPS * 32) knn_tile_kernel(co
         const int cz1 = cell_coord(__fadd_ru(zmax, R), g.lo[2], g.inv_h, g.n[2]);
         const uint32_t nyr = (uint32_t)(cy1 - cy0 + 1);
         const uint32_t nrows = nyr * (uint32_t)(cz1 - cz0 + 1);
-        if (nrows > 32u) { slow |= active; continue; }
+        if (nrows > 32u) {
+            slow |= active;
+            if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
+            continue;
+        }
         uint32_t s = 0, len = 0;
         if ((uint32_t)lane < nrows) {
             const int rz = cz0 + (int)((uint32_t)lane / nyr), ry = cy0 + (int)((uint32_t)lane % nyr);
@@ -367,125 +408,126 @@ __global__ void __launch_bounds__(TileCfg<NSORT>::WARPS * 32) knn_tile_kernel(co
         }
         const uint32_t C = __shfl_sync(kFull, off, 31);
         off -= len;
-        if (C > (uint32_t)Cfg::CMAX) { slow |= active; continue; }   // dense spot: the generic routine adapts its ball
+        const uint32_t C8 = (C + 7u) & ~7u;
+        if (C8 > (uint32_t)Cfg::CMAX) {   // dense spot: the generic routine adapts its ball
+            slow |= active;
+            if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
+            continue;
+        }
 
         // ---- stage the region: one 1-D TMA bulk copy per row, all rows in flight at once ---------
         __syncwarp();
         if (lane == 0) { ptx::fence_proxy_async_smem(); ptx::mbarrier_arrive_expect_tx(bar, C * 16u); }
         __syncwarp();
         if (len) ptx::bulk_g2s(stage + off, g.pts + s, len * 16u, bar);
+        // pad to a multiple of 8 with records no query accepts (d2 = +inf)
+        if (C + (uint32_t)lane < C8) stage[C + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
         ptx::mbarrier_wait(bar, parity);
         parity ^= 1u;
+        __syncwarp();
 
         // ---- scan: every candidate is read once per warp (broadcast) and tested by all lanes ------
         // accept iff d2 <= t2 with t2 strictly inside R^2, so every accepted point is in the region
         const float t2 = mine ? __fmul_rd(__fmul_rd(R, R), 0.9999f) : -1.f;
         uint32_t* const wbase = list + lane;
-        // shared-memory byte address of the lane's next free entry: advances by one stride per
-        // survivor, also past the end (the store is then suppressed, the count stays exact)
+        // shared-memory byte address of the lane's next free entry: advances by one stride per survivor;
+        // clamped once per batch of 8 to entry NLOAD + 1 (so the count saturates at NLOAD + 1 = overflow)
         const uint32_t waddr0 = ptx::smem_addr(wbase);
-        const uint32_t wend = waddr0 + LCAP * S * 4;
+        const uint32_t wclamp = waddr0 + (NLOAD + 1) * S * 4;
         uint32_t waddr = waddr0;
         // branch-free append (the compiler turns the equivalent C++ into a divergent branch per candidate)
 #define PGEOF_TILE_APPEND(D2, SLOT)                                                           \
-        asm volatile("{\n\t.reg .pred p, q;\n\t"                                              \
+        asm volatile("{\n\t.reg .pred p;\n\t"                                                 \
                      "setp.le.f32 p, %1, %2;\n\t"                                             \
-                     "setp.lt.and.u32 q, %0, %3, p;\n\t"                                      \
-                     "@q st.shared.u32 [%0], %4;\n\t"                                         \
-                     "@p add.u32 %0, %0, %5;\n\t}"                                            \
+                     "@p st.shared.u32 [%0], %3;\n\t"                                         \
+                     "@p add.u32 %0, %0, %4;\n\t}"                                            \
                      : "+r"(waddr)                                                            \
-                     : "f"(D2), "f"(t2), "r"(wend), "r"((__float_as_uint(D2) & ~Cfg::SLOT_MASK) | (SLOT)), "n"(S * 4));
-        {
-            uint32_t c = 0;
-            for (; c + 8 <= C; c += 8) {
-                float d[8];
+                     : "f"(D2), "f"(t2), "r"((__float_as_uint(D2) & ~Cfg::SLOT_MASK) | (SLOT)), "n"(S * 4));
+        for (uint32_t c = 0; c < C8; c += 8) {
+            float d[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const float4 p = stage[c + i]; d[i] = sqdist_f32(qx, qy, qz, p.x, p.y, p.z); }
+            for (int i = 0; i < 8; ++i) { const float4 p = stage[c + i]; d[i] = sqdist_f32(qx, qy, qz, p.x, p.y, p.z); }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) PGEOF_TILE_APPEND(d[i], c + i)
-            }
-            for (; c < C; ++c) {
-                const float4 p = stage[c];
-                const float d = sqdist_f32(qx, qy, qz, p.x, p.y, p.z);
-                PGEOF_TILE_APPEND(d, c)
-            }
+            for (int i = 0; i < 8; ++i) PGEOF_TILE_APPEND(d[i], c + i)
+            waddr = min(waddr, wclamp);
         }
 #undef PGEOF_TILE_APPEND
         __syncwarp();
         const uint32_t cnt = (waddr - waddr0) / (S * 4);
-        bool ok = mine && cnt >= k && cnt <= (uint32_t)LCAP;
-        __syncwarp();
+        bool ok = mine && cnt >= k && cnt <= (uint32_t)NLOAD;
+        if (a.stats) {
+            const unsigned sh = __ballot_sync(kFull, mine && cnt < k), ov = __ballot_sync(kFull, mine && cnt > (uint32_t)NLOAD);
+            const uint32_t sv = __reduce_add_sync(kFull, mine ? cnt : 0u);
+            if (lane == 0) {
+                atomicAdd(a.stats + ST_SHORT, (unsigned long long)__popc(sh));
+                atomicAdd(a.stats + ST_OVER, (unsigned long long)__popc(ov));
+                atomicAdd(a.stats + ST_PASSES, 1ull);
+                atomicAdd(a.stats + ST_CANDS, (unsigned long long)C);
+                atomicAdd(a.stats + ST_SURV, (unsigned long long)sv);
+            }
+        }
 
-        // ---- trim the list to [k, NSORT] entries: per-lane counting bisection on the entry word ----
-        // (entries order by their top 21 bits = truncated d2; everything sharing a truncated value is
-        // kept or dropped together, so the kept set is always a prefix of the true (d2, index) order)
-        uint32_t m = cnt;
-        bool pending = ok && cnt > (uint32_t)NSORT;
-        if (__any_sync(kFull, pending)) {
-            const uint32_t maxcnt = __reduce_max_sync(kFull, pending ? cnt : 0u);
-            // thresholds u: keep an entry iff (entry >> SLOT_BITS) < u
-            uint32_t lo = 0, hi = (__float_as_uint(t2) >> Cfg::SLOT_BITS) + 1u, thr = hi;
-            float cur_cnt = (float)cnt, cur_d2 = t2;
-            const float want = 0.5f * (float)(k + NSORT);
-            for (int it = 0; it < 28 && __any_sync(kFull, pending); ++it) {
-                uint32_t mid = lo + (hi - lo) / 2;
-                if (it < 4) {
-                    const float gd2 = cur_d2 * exp2f(0.6666667f * log2f(want / cur_cnt));
-                    const uint32_t guess = (__float_as_uint(gd2) >> Cfg::SLOT_BITS) + 1u;
-                    if (guess > lo && guess < hi) mid = guess;
-                }
-                const uint32_t cut_word = mid << Cfg::SLOT_BITS;
-                uint32_t n = 0;
-#pragma unroll 8
-                for (uint32_t i = 0; i < maxcnt; ++i) n += (i < cnt && wbase[i * S] < cut_word) ? 1u : 0u;
-                if (pending) {
-                    if (n < k) lo = mid;
-                    else if (n > (uint32_t)NSORT) hi = mid;
-                    else { thr = mid; m = n; pending = false; }
-                    cur_cnt = fmaxf((float)n, 0.5f);
-                    cur_d2 = __uint_as_float((mid << Cfg::SLOT_BITS) - 1u);
-                    if (pending && hi - lo <= 1u) { pending = false; ok = false; }   // too many (near-)ties at the window
+        // ---- sort: one thread per row, 32-bit keys in registers ---------------------------------
+        uint32_t dropped;
+        uint32_t bad = 0;
+        {
+            uint32_t v[NLOAD];
+#pragma unroll
+            for (int i = 0; i < NLOAD; ++i) {
+                const uint32_t w = wbase[i * S];
+                v[i] = (uint32_t)i < cnt ? w : 0xffffffffu;
+            }
+            __syncwarp();                      // the lists are dead: their memory becomes the d2 plane
+            dropped = select_sort_network<NOUT, NEXTRA>(v);
+            // rebuild the exact (d2, index) pairs in sorted order.  Keys that share their truncated
+            // distance may be out of order: remember it, the row is repaired in shared memory below.
+            // plane[i * S + lane] = i-th neighbour of this lane's row
+            uint32_t* plane_d = list + lane;
+            uint32_t pd = 0, pi = 0;
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) {
+                const float4 p = stage[v[i] & Cfg::SLOT_MASK];
+                const uint32_t d = __float_as_uint(sqdist_f32(qx, qy, qz, p.x, p.y, p.z));
+                const uint32_t id = __float_as_uint(p.w);
+                if (i > 0) bad |= ((uint32_t)i < cnt && (d < pd || (d == pd && id < pi))) ? 1u : 0u;
+                pd = d; pi = id;
+                plane_d[i * S] = d;
+                v[i] = id;
+            }
+            __syncwarp();                      // the staged candidates are dead: index plane
+            uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
+#pragma unroll
+            for (int i = 0; i < NOUT; ++i) plane_i[i * S] = v[i];
+        }
+        {
+            uint32_t* plane_d = list + lane;
+            uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
+            // a dropped key that shares the truncated distance of the k-th neighbour may belong before it
+            const bool tie = ok && dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) == (plane_d[(k - 1) * S] >> Cfg::SLOT_BITS);
+            if (tie) ok = false;
+            if (a.stats) {
+                const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && bad);
+                if (lane == 0) {
+                    atomicAdd(a.stats + ST_TIE, (unsigned long long)__popc(tm));
+                    atomicAdd(a.stats + ST_FIXED, (unsigned long long)__popc(fm));
                 }
             }
-            if (pending) { pending = false; ok = false; }
-            // compact the kept entries to the front of the list (in place: writes trail reads)
-            const bool cut = ok && m < cnt;
-            if (__any_sync(kFull, cut)) {
-                const uint32_t cut_word = thr << Cfg::SLOT_BITS;
-                uint32_t pos = 0;
-#pragma unroll 4
-                for (uint32_t i = 0; i < maxcnt; ++i) {
-                    if (cut && i < cnt) {
-                        const uint32_t w = wbase[i * S];
-                        if (w < cut_word) { wbase[pos * S] = w; ++pos; }
+            if (ok && bad) {                   // insertion sort of an almost sorted row on the exact (d2, index) order
+                const uint32_t nfix = min(cnt, (uint32_t)NOUT);
+                for (uint32_t i = 1; i < nfix; ++i) {
+                    const uint32_t d = plane_d[i * S], id = plane_i[i * S];
+                    uint32_t j = i;
+                    while (j > 0) {
+                        const uint32_t qd = plane_d[(j - 1) * S], qi = plane_i[(j - 1) * S];
+                        if (qd < d || (qd == d && qi < id)) break;
+                        plane_d[j * S] = qd; plane_i[j * S] = qi;
+                        --j;
                     }
+                    if (j != i) { plane_d[j * S] = d; plane_i[j * S] = id; }
                 }
             }
         }
         slow |= __ballot_sync(kFull, mine && !ok);
-        __syncwarp();
-
-        // ---- rebuild the exact keys and sort them: one thread per row, all in registers ---------
-        {
-            u64 v[NSORT];
-#pragma unroll
-            for (int i = 0; i < NSORT; ++i) {
-                const bool live = ok && (uint32_t)i < m;
-                const uint32_t slot = live ? (wbase[i * S] & Cfg::SLOT_MASK) : 0u;
-                const float4 p = stage[slot];
-                v[i] = live ? make_key(sqdist_f32(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w)) : kKeyMax;
-            }
-            RegOddEvenSort<NSORT, 0, NSORT>::run(v);
-            // transpose through shared memory (the staged candidates and the lists are dead now):
-            // plane[i * S + lane] = i-th neighbour of this lane's row
-            __syncwarp();
-            uint32_t* plane_d = list + lane;
-            uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
-#pragma unroll
-            for (int i = 0; i < NSORT; ++i) {
-                if ((uint32_t)i < k) { plane_d[i * S] = (uint32_t)(v[i] >> 32); plane_i[i * S] = (uint32_t)v[i]; }
-            }
-        }
         __syncwarp();
         // ---- write the finished rows, one coalesced row at a time ---------------------------------
         {
@@ -518,7 +560,7 @@ __global__ void __launch_bounds__(TileCfg<NSORT>::WARPS * 32) knn_tile_kernel(co
         u64 tau;
         const uint32_t c = knn_collect<Cfg::GEN_CAP>(g, sx, sy, sz, k, a.target, keybuf, lane, &tau);
         u64 v[M];
-        select_and_sort<NSORT, Cfg::GEN_CAP>(keybuf, c, tau, k, lane, v);
+        select_and_sort<NOUT, Cfg::GEN_CAP>(keybuf, c, tau, k, lane, v);
         write_knn_row<M>(a, rowq, k, v, lane);
         __syncwarp();
     }
@@ -540,12 +582,12 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
-template <int NSORT>
+template <int NOUT, int NEXTRA>
 int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
-    using Cfg = TileCfg<NSORT>;
+    using Cfg = TileCfg<NOUT, NEXTRA>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
-    auto kern = knn_tile_kernel<NSORT>;
+    auto kern = knn_tile_kernel<NOUT, NEXTRA>;
     PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
     {
@@ -555,6 +597,9 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     PGEOF_LAUNCH_CHECK();
     return PGEOF_OK;
 }
+
+// survivors the tile kernel's sorting network absorbs for a given k
+inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= 52 ? 96 : 128); }
 
 template <int MODE>
 int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, cudaStream_t stream)
@@ -585,9 +630,11 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     float target = 0.f;
     const bool tile = mode == SEARCH_KNN && k <= 64 && env_float("PGEOF_KNN_TILE", 1.f) != 0.f;
     if (mode == SEARCH_KNN) {
-        // ball seeded to hold k + 2..2.5 sigma + 2 points.  Tile path: cell edge h slightly above that
-        // ball's radius so that a warp's region is 3 x 3 (y, z) rows, cells 4x finer along x.
-        target = (float)k + (tile ? 2.5f : 2.f) * std::sqrt((float)k) + 2.f;
+        // ball seeded to hold k + z sigma + 2 points.  Tile path: z balances the two ways a query leaves the
+        // fast path (fewer than k survivors / more than the sorting network absorbs); cell edge h slightly
+        // above that ball's radius so that a warp's region is 3 x 3 (y, z) rows, cells 4x finer along x.
+        target = (float)k + (tile ? env_float("PGEOF_KNN_Z", 2.9f) : 2.f) * std::sqrt((float)k) + 2.f;
+        if (tile) target = std::min(target, 0.5f * (float)(k + tile_nload(k)));
         const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", tile ? 0.33f : 0.25f));
         PGEOF_TRY(grid_build(data, n_data, 0.f, occ, tile ? (int)env_float("PGEOF_KNN_XF", 4.f) : 1, stream, &grid));
     } else {
@@ -599,8 +646,30 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     const float4* qrec;
     if (query == data && n_query == n_data) qrec = grid.view.pts;   // self query: reuse the sorted cloud
     else { PGEOF_TRY(grid_sort_queries(grid, query, n_query, stream, &qsorted)); qrec = qsorted.as<float4>(); }
-    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr};
-    if (tile) return k <= 32 ? launch_tile<32>(grid.view, a, stream) : launch_tile<64>(grid.view, a, stream);
+    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr};
+    if (tile) {
+        DeviceBuffer stats;
+        const bool want_stats = env_float("PGEOF_KNN_STATS", 0.f) != 0.f;
+        if (want_stats) {
+            PGEOF_TRY(stats.alloc(ST_N * sizeof(unsigned long long), stream));
+            PGEOF_CUDA(cudaMemsetAsync(stats.ptr, 0, ST_N * sizeof(unsigned long long), stream));
+            a.stats = stats.as<unsigned long long>();
+        }
+        int st;
+        if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
+        else if (k <= 52) st = launch_tile<64, 32>(grid.view, a, stream);
+        else st = launch_tile<64, 64>(grid.view, a, stream);
+        if (st == PGEOF_OK && want_stats) {
+            unsigned long long h[ST_N];
+            PGEOF_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
+            PGEOF_CUDA(cudaStreamSynchronize(stream));
+            std::fprintf(stderr, "[pgeof knn tile] n=%zu k=%u target=%.1f: slow short=%llu over=%llu tie=%llu region=%llu | fixed rows=%llu "
+                         "passes=%llu candidates/pass=%.1f survivors/query=%.1f\n", n_query, k, target, h[ST_SHORT], h[ST_OVER], h[ST_TIE],
+                         h[ST_REGION], h[ST_FIXED], h[ST_PASSES], (double)h[ST_CANDS] / (double)std::max(h[ST_PASSES], 1ull),
+                         (double)h[ST_SURV] / (double)n_query);
+        }
+        return st;
+    }
     switch (mode) {
         case SEARCH_KNN: return dispatch_search<SEARCH_KNN>(k, grid.view, a, stream);
         case SEARCH_RADIUS: return dispatch_search<SEARCH_RADIUS>(k, grid.view, a, stream);

@@ -225,22 +225,22 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&v)[M], int lane)
     }
 }
 
-// Thread-local Batcher odd-even merge sort of N keys held in registers (N a power of two).
-// Every index is a compile-time constant after unrolling, so v[] never leaves the register
-// file; a compare-exchange is 2 ISETP + 4 SEL with no shuffles, and the 32 lanes of a warp sort
-// 32 independent lists at once (N = 64: 543 compare-exchanges).
+// Thread-local sorting networks on N 32-bit keys held in registers.  Every index is a compile-time
+// constant after unrolling, so v[] never leaves the register file; a compare-exchange is one
+// unsigned min / max pair (no predicates, no shuffles) and the 32 lanes of a warp sort 32
+// independent lists at once.  Batcher odd-even merge sort: 191 compare-exchanges for 32 keys,
+// 161 more to merge two sorted runs of 32.
 template <int N>
-__device__ __forceinline__ void reg_cmpswap(u64 (&v)[N], int i, int j)
+__device__ __forceinline__ void reg_cmpswap(uint32_t (&v)[N], int i, int j)
 {
-    const u64 a = v[i], b = v[j];
-    const bool sw = a > b;
-    v[i] = sw ? b : a;
-    v[j] = sw ? a : b;
+    const uint32_t a = v[i], b = v[j];
+    v[i] = min(a, b);
+    v[j] = max(a, b);
 }
 
 template <int N, int LO, int CNT, int R>
 struct RegOddEvenMerge {
-    static __device__ __forceinline__ void run(u64 (&v)[N])
+    static __device__ __forceinline__ void run(uint32_t (&v)[N])
     {
         constexpr int STEP = R * 2;
         if constexpr (STEP < CNT) {
@@ -256,12 +256,26 @@ struct RegOddEvenMerge {
 
 template <int N, int LO, int CNT>
 struct RegOddEvenSort {
-    static __device__ __forceinline__ void run(u64 (&v)[N])
+    static __device__ __forceinline__ void run(uint32_t (&v)[N])
     {
         if constexpr (CNT > 1) {
             RegOddEvenSort<N, LO, CNT / 2>::run(v);
             RegOddEvenSort<N, LO + CNT / 2, CNT / 2>::run(v);
             RegOddEvenMerge<N, LO, CNT, 1>::run(v);
+        }
+    }
+};
+
+// v[LO, LO+CNT) is bitonic -> ascending (CNT a power of two)
+template <int N, int LO, int CNT>
+struct RegBitonicMerge {
+    static __device__ __forceinline__ void run(uint32_t (&v)[N])
+    {
+        if constexpr (CNT > 1) {
+#pragma unroll
+            for (int i = 0; i < CNT / 2; ++i) reg_cmpswap<N>(v, LO + i, LO + i + CNT / 2);
+            RegBitonicMerge<N, LO, CNT / 2>::run(v);
+            RegBitonicMerge<N, LO + CNT / 2, CNT / 2>::run(v);
         }
     }
 };
