@@ -70,12 +70,15 @@ enum { ST_SHORT = 0, ST_OVER, ST_TIE, ST_REGION, ST_FIXED, ST_PASSES, ST_CANDS, 
 // ---------------------------------------------------------------------------------------
 template <int CAP>
 __device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, float qy, float qz, uint32_t k, float target,
-                                                u64* keybuf, int lane, u64* tau_out)
+                                                u64* keybuf, int lane, u64* tau_out, float r_hint = 0.f)
 {
-    uint32_t n27, cells27;
-    block27_count(g, qx, qy, qz, lane, &n27, &cells27);
-    const float rho = fmaxf((float)n27, 1.f) / ((float)max(cells27, 1u) * g.hx * g.h * g.h);
-    float R = cbrtf(target / (4.18879f * rho)) + bbox_distance(g, qx, qy, qz);
+    float R = r_hint;
+    if (!(r_hint > 0.f)) {   // no hint (warp uniform): seed the ball from the density of the 3x3x3 block
+        uint32_t n27, cells27;
+        block27_count(g, qx, qy, qz, lane, &n27, &cells27);
+        const float rho = fmaxf((float)n27, 1.f) / ((float)max(cells27, 1u) * g.hx * g.h * g.h);
+        R = cbrtf(target / (4.18879f * rho)) + bbox_distance(g, qx, qy, qz);
+    }
     float Rg = R, Rg_hi = 0.f;
     u64 tau_lo = 0, tau_hi = 0;
     bool have_lo = false, have_hi = false;
@@ -269,7 +272,7 @@ struct TileCfg {
     static constexpr int BAR_BYTES = 16;
     static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
     static constexpr int GEN_CAP = 256;            // key buffer of the generic fallback (aliases the staging area)
-    static constexpr int MAX_PASSES = 4;           // (y, z) rows one warp may straddle before it falls back
+    static constexpr int MAX_PASSES = 6;           // passes ((y, z) rows straddled, halved regions) before a warp falls back
     // a list entry / sort key is (bits(d2) & ~SLOT_MASK) | staged slot: 22 bits of distance order the
     // network, the slot finds the candidate again when the exact (d2, index) pair is rebuilt
     static constexpr uint32_t SLOT_BITS = 10;
@@ -335,85 +338,98 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
 
     unsigned remaining = __ballot_sync(kFull, valid);
     unsigned slow = 0;                       // lanes finished by the generic routine
+    float rhint = 0.f;                       // ... which starts from this radius (0: from the local density)
     for (int pass = 0; remaining; ++pass) {
         // ---- the lanes of this pass: queries in the (y, z) cell row of the first remaining lane ----
         const int leader = __ffs(remaining) - 1;
         const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
-        const unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow);
+        unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow);
         remaining &= ~active;
         if (pass >= Cfg::MAX_PASSES) {
             slow |= active;
             if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
             continue;
         }
-        const bool mine = (active >> lane) & 1u;
 
-        // ---- bounding box of the active queries -----------------------------------------------
-        const float xmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qx) : 0xffffffffu));
-        const float xmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qx) : 0u));
-        const float ymin = o2f(__reduce_min_sync(kFull, mine ? f2o(qy) : 0xffffffffu));
-        const float ymax = o2f(__reduce_max_sync(kFull, mine ? f2o(qy) : 0u));
-        const float zmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qz) : 0xffffffffu));
-        const float zmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qz) : 0u));
-        const int cxa = __reduce_min_sync(kFull, mine ? cqx : 0x7fffffff);
-        const int cxb = __reduce_max_sync(kFull, mine ? cqx : -1);
-        const int cy = __shfl_sync(kFull, cqy, leader), cz = __shfl_sync(kFull, cqz, leader);
+        // ---- region of the active queries; a region too large to stage is halved along x ---------
+        float R = 0.f;
+        uint32_t s = 0, len = 0, off = 0, C = 0, C8 = 0;
+        bool mine = false;
+        for (int split = 0;; ++split) {
+            mine = (active >> lane) & 1u;
+            // bounding box of the active queries
+            const float xmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qx) : 0xffffffffu));
+            const float xmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qx) : 0u));
+            const float ymin = o2f(__reduce_min_sync(kFull, mine ? f2o(qy) : 0xffffffffu));
+            const float ymax = o2f(__reduce_max_sync(kFull, mine ? f2o(qy) : 0u));
+            const float zmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qz) : 0xffffffffu));
+            const float zmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qz) : 0u));
+            const int cxa = __reduce_min_sync(kFull, mine ? cqx : 0x7fffffff);
+            const int cxb = __reduce_max_sync(kFull, mine ? cqx : -1);
+            const int cy = __shfl_sync(kFull, cqy, leader), cz = __shfl_sync(kFull, cqz, leader);
 
-        // ---- density of the block around them -> search radius R ------------------------------
-        float R;
-        {
-            const int bx0 = max(cxa - g.xf, 0), bx1 = min(cxb + g.xf, g.n[0] - 1);
-            int c = 0, nc = 0;
-            if (lane < 9) {
-                const int by = cy + lane % 3 - 1, bz = cz + lane / 3 - 1;
-                if (by >= 0 && by < g.n[1] && bz >= 0 && bz < g.n[2]) {
-                    const uint32_t rb = ((uint32_t)bz * (uint32_t)g.n[1] + (uint32_t)by) * (uint32_t)g.n[0];
-                    c = (int)(__ldg(g.cell_start + rb + bx1 + 1) - __ldg(g.cell_start + rb + bx0));
-                    nc = bx1 - bx0 + 1;
+            // density of the block around them -> search radius R
+            {
+                const int bx0 = max(cxa - g.xf, 0), bx1 = min(cxb + g.xf, g.n[0] - 1);
+                int c = 0, nc = 0;
+                if (lane < 9) {
+                    const int by = cy + lane % 3 - 1, bz = cz + lane / 3 - 1;
+                    if (by >= 0 && by < g.n[1] && bz >= 0 && bz < g.n[2]) {
+                        const uint32_t rb = ((uint32_t)bz * (uint32_t)g.n[1] + (uint32_t)by) * (uint32_t)g.n[0];
+                        c = (int)(__ldg(g.cell_start + rb + bx1 + 1) - __ldg(g.cell_start + rb + bx0));
+                        nc = bx1 - bx0 + 1;
+                    }
                 }
+                c = __reduce_add_sync(kFull, c);
+                nc = __reduce_add_sync(kFull, nc);
+                const float rho = fmaxf((float)c, 1.f) / ((float)max(nc, 1) * g.hx * g.h * g.h);
+                R = cbrtf(a.target / (4.18879f * rho));
             }
-            c = __reduce_add_sync(kFull, c);
-            nc = __reduce_add_sync(kFull, nc);
-            const float rho = fmaxf((float)c, 1.f) / ((float)max(nc, 1) * g.hx * g.h * g.h);
-            R = cbrtf(a.target / (4.18879f * rho));
-        }
 
-        // ---- candidate region: cells meeting the dilated box; one contiguous span per (y, z) row ---
-        const int cx0 = cell_coord(__fsub_rd(xmin, R), g.lo[0], g.inv_hx, g.n[0]);
-        const int cx1 = cell_coord(__fadd_ru(xmax, R), g.lo[0], g.inv_hx, g.n[0]);
-        const int cy0 = cell_coord(__fsub_rd(ymin, R), g.lo[1], g.inv_h, g.n[1]);
-        const int cy1 = cell_coord(__fadd_ru(ymax, R), g.lo[1], g.inv_h, g.n[1]);
-        const int cz0 = cell_coord(__fsub_rd(zmin, R), g.lo[2], g.inv_h, g.n[2]);
-        const int cz1 = cell_coord(__fadd_ru(zmax, R), g.lo[2], g.inv_h, g.n[2]);
-        const uint32_t nyr = (uint32_t)(cy1 - cy0 + 1);
-        const uint32_t nrows = nyr * (uint32_t)(cz1 - cz0 + 1);
-        if (nrows > 32u) {
-            slow |= active;
-            if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
-            continue;
-        }
-        uint32_t s = 0, len = 0;
-        if ((uint32_t)lane < nrows) {
-            const int rz = cz0 + (int)((uint32_t)lane / nyr), ry = cy0 + (int)((uint32_t)lane % nyr);
-            const uint32_t rb = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
-            s = __ldg(g.cell_start + rb + cx0);
-            len = __ldg(g.cell_start + rb + cx1 + 1) - s;
-        }
-        // exclusive prefix of the span lengths = where each row lands in the staging area
-        uint32_t off = len;
+            // candidate region: cells meeting the dilated box; one contiguous span per (y, z) row
+            const int cx0 = cell_coord(__fsub_rd(xmin, R), g.lo[0], g.inv_hx, g.n[0]);
+            const int cx1 = cell_coord(__fadd_ru(xmax, R), g.lo[0], g.inv_hx, g.n[0]);
+            const int cy0 = cell_coord(__fsub_rd(ymin, R), g.lo[1], g.inv_h, g.n[1]);
+            const int cy1 = cell_coord(__fadd_ru(ymax, R), g.lo[1], g.inv_h, g.n[1]);
+            const int cz0 = cell_coord(__fsub_rd(zmin, R), g.lo[2], g.inv_h, g.n[2]);
+            const int cz1 = cell_coord(__fadd_ru(zmax, R), g.lo[2], g.inv_h, g.n[2]);
+            const uint32_t nyr = (uint32_t)(cy1 - cy0 + 1);
+            const uint32_t nrows = nyr * (uint32_t)(cz1 - cz0 + 1);
+            bool fits = nrows <= 32u;
+            if (fits) {
+                s = 0; len = 0;
+                if ((uint32_t)lane < nrows) {
+                    const int rz = cz0 + (int)((uint32_t)lane / nyr), ry = cy0 + (int)((uint32_t)lane % nyr);
+                    const uint32_t rb = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
+                    s = __ldg(g.cell_start + rb + cx0);
+                    len = __ldg(g.cell_start + rb + cx1 + 1) - s;
+                }
+                // exclusive prefix of the span lengths = where each row lands in the staging area
+                off = len;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFull, off, o);
-            if (lane >= o) off += t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, off, o);
+                    if (lane >= o) off += t;
+                }
+                C = __shfl_sync(kFull, off, 31);
+                off -= len;
+                C8 = (C + 7u) & ~7u;
+                fits = C8 <= (uint32_t)Cfg::CMAX;
+            }
+            if (fits) break;
+            const int na = __popc(active);
+            if (na < 2 || split >= 3 || nrows > 32u) {   // dense spot: the generic routine adapts its ball
+                slow |= active;
+                if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)na);
+                active = 0;
+                break;
+            }
+            // keep the lower half of the lanes (cell-sorted, so the lower half along x); the rest waits for a later pass
+            const unsigned keep = __ballot_sync(kFull, mine && __popc(active & lanemask_lt()) < na / 2);
+            remaining |= active & ~keep;
+            active = keep;
         }
-        const uint32_t C = __shfl_sync(kFull, off, 31);
-        off -= len;
-        const uint32_t C8 = (C + 7u) & ~7u;
-        if (C8 > (uint32_t)Cfg::CMAX) {   // dense spot: the generic routine adapts its ball
-            slow |= active;
-            if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
-            continue;
-        }
+        if (!active) continue;
 
         // ---- stage the region: one 1-D TMA bulk copy per row, all rows in flight at once ---------
         __syncwarp();
@@ -455,6 +471,8 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         __syncwarp();
         const uint32_t cnt = (waddr - waddr0) / (S * 4);
         bool ok = mine && cnt >= k && cnt <= (uint32_t)NLOAD;
+        // radius the generic routine starts from if this lane leaves the fast path: scaled by the count seen here
+        if (mine) rhint = R * (cnt < k ? fminf(cbrtf(1.25f * a.target / fmaxf((float)cnt, 2.f)), 3.f) : (cnt > (uint32_t)NLOAD ? 0.88f : 1.f));
         if (a.stats) {
             const unsigned sh = __ballot_sync(kFull, mine && cnt < k), ov = __ballot_sync(kFull, mine && cnt > (uint32_t)NLOAD);
             const uint32_t sv = __reduce_add_sync(kFull, mine ? cnt : 0u);
@@ -469,7 +487,7 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
 
         // ---- sort: one thread per row, 32-bit keys in registers ---------------------------------
         uint32_t dropped;
-        uint32_t bad = 0;
+        uint32_t bad[M] = {};                  // bit i: sorted entry i precedes entry i - 1 in the exact order
         {
             uint32_t v[NLOAD];
 #pragma unroll
@@ -489,7 +507,7 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
                 const float4 p = stage[v[i] & Cfg::SLOT_MASK];
                 const uint32_t d = __float_as_uint(sqdist_f32(qx, qy, qz, p.x, p.y, p.z));
                 const uint32_t id = __float_as_uint(p.w);
-                if (i > 0) bad |= ((uint32_t)i < cnt && (d < pd || (d == pd && id < pi))) ? 1u : 0u;
+                if (i > 0) bad[i / 32] |= ((uint32_t)i < cnt && (d < pd || (d == pd && id < pi))) ? (1u << (i % 32)) : 0u;
                 pd = d; pi = id;
                 plane_d[i * S] = d;
                 v[i] = id;
@@ -506,16 +524,29 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
             const bool tie = ok && dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) == (plane_d[(k - 1) * S] >> Cfg::SLOT_BITS);
             if (tie) ok = false;
             if (a.stats) {
-                const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && bad);
+                const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && (bad[0] | bad[M - 1]));
                 if (lane == 0) {
                     atomicAdd(a.stats + ST_TIE, (unsigned long long)__popc(tm));
                     atomicAdd(a.stats + ST_FIXED, (unsigned long long)__popc(fm));
                 }
             }
-            if (ok && bad) {                   // insertion sort of an almost sorted row on the exact (d2, index) order
+            uint32_t any_bad = 0;
+#pragma unroll
+            for (int r = 0; r < M; ++r) any_bad |= bad[r];
+            if (ok && any_bad) {
+                // insertion sort on the exact (d2, index) order, from the first inversion to the end of the tie
+                // group (equal truncated distance) that holds the last one: everything else is in order already
+                uint32_t first = 0, last = 0;
+#pragma unroll
+                for (int r = M - 1; r >= 0; --r) if (bad[r]) first = r * 32 + __ffs(bad[r]) - 1;
+#pragma unroll
+                for (int r = 0; r < M; ++r) if (bad[r]) last = r * 32 + 31 - __clz(bad[r]);
                 const uint32_t nfix = min(cnt, (uint32_t)NOUT);
-                for (uint32_t i = 1; i < nfix; ++i) {
+                uint32_t pt = 0;
+                for (uint32_t i = first; i < nfix; ++i) {
                     const uint32_t d = plane_d[i * S], id = plane_i[i * S];
+                    if (i > last && (d >> Cfg::SLOT_BITS) != pt) break;
+                    pt = d >> Cfg::SLOT_BITS;
                     uint32_t j = i;
                     while (j > 0) {
                         const uint32_t qd = plane_d[(j - 1) * S], qi = plane_i[(j - 1) * S];
@@ -533,10 +564,10 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         {
             const uint32_t* plane_d = list;
             const uint32_t* plane_i = reinterpret_cast<const uint32_t*>(stage);
-            unsigned okm = __ballot_sync(kFull, ok);
-            while (okm) {
-                const int q = __ffs(okm) - 1;
-                okm &= okm - 1;
+            const unsigned okm = __ballot_sync(kFull, ok);
+#pragma unroll 4
+            for (int q = 0; q < 32; ++q) {
+                if (!((okm >> q) & 1u)) continue;
                 const uint32_t rowq = __shfl_sync(kFull, row, q);
                 uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)rowq * k;
                 float* d2 = a.sqr_dist + (size_t)rowq * k;
@@ -557,8 +588,9 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         slow &= slow - 1;
         const float sx = __shfl_sync(kFull, qx, q), sy = __shfl_sync(kFull, qy, q), sz = __shfl_sync(kFull, qz, q);
         const uint32_t rowq = __shfl_sync(kFull, row, q);
+        const float rh = __shfl_sync(kFull, rhint, q);
         u64 tau;
-        const uint32_t c = knn_collect<Cfg::GEN_CAP>(g, sx, sy, sz, k, a.target, keybuf, lane, &tau);
+        const uint32_t c = knn_collect<Cfg::GEN_CAP>(g, sx, sy, sz, k, a.target, keybuf, lane, &tau, rh);
         u64 v[M];
         select_and_sort<NOUT, Cfg::GEN_CAP>(keybuf, c, tau, k, lane, v);
         write_knn_row<M>(a, rowq, k, v, lane);
