@@ -60,6 +60,8 @@ struct SearchArgs {
     float* sqr_dist;
     uint32_t* nn_ptr;        // RADIUS_COUNT: per-row counts out; RADIUS_CSR: row offsets in
     unsigned long long* stats;   // optional tile-kernel counters (PGEOF_KNN_STATS=1), else null
+    uint2* slow_list;        // tile kernel: (query position, bits(radius hint)) of the queries left to knn_slow_kernel
+    uint32_t* slow_count;
 };
 
 // tile-kernel counters: why queries left the fast path, and how much work the fast path did
@@ -271,14 +273,12 @@ struct TileCfg {
     static constexpr int STAGE_BYTES = CMAX * 16;
     static constexpr int BAR_BYTES = 16;
     static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
-    static constexpr int GEN_CAP = 256;            // key buffer of the generic fallback (aliases the staging area)
     static constexpr int MAX_PASSES = 6;           // passes ((y, z) rows straddled, halved regions) before a warp falls back
     // a list entry / sort key is (bits(d2) & ~SLOT_MASK) | staged slot: 22 bits of distance order the
     // network, the slot finds the candidate again when the exact (d2, index) pair is rebuilt
     static constexpr uint32_t SLOT_BITS = 10;
     static constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1;
     static_assert(CMAX % 8 == 0 && CMAX <= (1 << SLOT_BITS), "slot field too small");
-    static_assert(STAGE_BYTES >= GEN_CAP * 8, "fallback key buffer must fit the staging area");
     static_assert(LIST_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "alignment");
     static_assert(NOUT * STRIDE * 4 <= LIST_BYTES && NOUT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
     static_assert((1 << SLOT_BITS) * 16 <= SMEM_WARP_BYTES, "a padded slot must stay inside the warp's shared memory");
@@ -581,19 +581,34 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         __syncwarp();
     }
 
-    // ---- generic per-query routine for the lanes the tile path could not finish ----------------
-    u64* keybuf = reinterpret_cast<u64*>(stage);
-    while (slow) {
-        const int q = __ffs(slow) - 1;
-        slow &= slow - 1;
-        const float sx = __shfl_sync(kFull, qx, q), sy = __shfl_sync(kFull, qy, q), sz = __shfl_sync(kFull, qz, q);
-        const uint32_t rowq = __shfl_sync(kFull, row, q);
-        const float rh = __shfl_sync(kFull, rhint, q);
+    // ---- queue the lanes the tile path could not finish for knn_slow_kernel --------------------
+    // (kept out of this kernel: the generic routine is large, rarely needed and latency bound; inlined here
+    // it evicted the sorting network from the instruction cache and ran at 1/8 occupancy)
+    if (slow) {
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(a.slow_count, (uint32_t)__popc(slow));
+        at = __shfl_sync(kFull, at, 0);
+        if ((slow >> lane) & 1u) a.slow_list[at + __popc(slow & lanemask_lt())] = make_uint2(base + lane, __float_as_uint(rhint));
+    }
+}
+
+// generic per-query routine (one warp per query) over the queries the tile kernel queued
+template <int NOUT>
+__global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g, const SearchArgs a)
+{
+    constexpr int M = NOUT / 32, CAP = 256;
+    __shared__ u64 keys[kWarps][CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* keybuf = keys[warp];
+    const uint32_t n = *a.slow_count, k = a.k;
+    for (uint32_t w = blockIdx.x * kWarps + warp; w < n; w += gridDim.x * kWarps) {
+        const uint2 rec = a.slow_list[w];
+        const float4 q4 = __ldg(a.queries + rec.x);
         u64 tau;
-        const uint32_t c = knn_collect<Cfg::GEN_CAP>(g, sx, sy, sz, k, a.target, keybuf, lane, &tau, rh);
+        const uint32_t c = knn_collect<CAP>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, __uint_as_float(rec.y));
         u64 v[M];
-        select_and_sort<NOUT, Cfg::GEN_CAP>(keybuf, c, tau, k, lane, v);
-        write_knn_row<M>(a, rowq, k, v, lane);
+        select_and_sort<NOUT, CAP>(keybuf, c, tau, k, lane, v);
+        write_knn_row<M>(a, __float_as_uint(q4.w), k, v, lane);
         __syncwarp();
     }
 }
@@ -625,7 +640,9 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     {
         KernelTimer timer("knn_search", stream);
         kern<<<blocks, Cfg::WARPS * 32, smem, stream>>>(g, a);
+        knn_slow_kernel<NOUT><<<148 * 4, kWarps * 32, 0, stream>>>(g, a);
     }
+    PGEOF_LAUNCH_CHECK();
     PGEOF_LAUNCH_CHECK();
     return PGEOF_OK;
 }
@@ -665,10 +682,10 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         // ball seeded to hold k + z sigma + 2 points.  Tile path: z balances the two ways a query leaves the
         // fast path (fewer than k survivors / more than the sorting network absorbs); cell edge h slightly
         // above that ball's radius so that a warp's region is 3 x 3 (y, z) rows, cells 4x finer along x.
-        target = (float)k + (tile ? env_float("PGEOF_KNN_Z", 2.9f) : 2.f) * std::sqrt((float)k) + 2.f;
+        target = (float)k + (tile ? env_float("PGEOF_KNN_Z", 2.6f) : 2.f) * std::sqrt((float)k) + 2.f;
         if (tile) target = std::min(target, 0.5f * (float)(k + tile_nload(k)));
-        const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", tile ? 0.33f : 0.25f));
-        PGEOF_TRY(grid_build(data, n_data, 0.f, occ, tile ? (int)env_float("PGEOF_KNN_XF", 4.f) : 1, stream, &grid));
+        const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", tile ? 0.28f : 0.25f));
+        PGEOF_TRY(grid_build(data, n_data, 0.f, occ, tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1, stream, &grid));
     } else {
         if (!(radius >= 0.f) || !std::isfinite(radius)) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
         const float edge = radius * env_float("PGEOF_RADIUS_CELL_SCALE", 1.0f);
@@ -678,9 +695,13 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     const float4* qrec;
     if (query == data && n_query == n_data) qrec = grid.view.pts;   // self query: reuse the sorted cloud
     else { PGEOF_TRY(grid_sort_queries(grid, query, n_query, stream, &qsorted)); qrec = qsorted.as<float4>(); }
-    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr};
+    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr, nullptr, nullptr};
     if (tile) {
-        DeviceBuffer stats;
+        DeviceBuffer stats, slow;
+        PGEOF_TRY(slow.alloc(16 + n_query * sizeof(uint2), stream));
+        a.slow_count = slow.as<uint32_t>();
+        a.slow_list = reinterpret_cast<uint2*>(slow.as<unsigned char>() + 16);
+        PGEOF_CUDA(cudaMemsetAsync(a.slow_count, 0, 16, stream));
         const bool want_stats = env_float("PGEOF_KNN_STATS", 0.f) != 0.f;
         if (want_stats) {
             PGEOF_TRY(stats.alloc(ST_N * sizeof(unsigned long long), stream));
