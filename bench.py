@@ -38,7 +38,7 @@ UNIT = "points/s"
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--points", type=int, default=10_000_000)
@@ -59,37 +59,75 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe).  In-process NVML
+    (two cheap queries every 25 ms from a thread); falls back to an `nvidia-smi -lms` child process."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "250"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _poll(self):
+        nv = self.nvml
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), sm, [bool(r & b) for b in bits]))
+            except Exception:
+                pass
+            time.sleep(0.025)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+            c = [x.strip() for x in line.split(",")]
+            if len(c) >= 7 and c[0].replace(".", "").isdigit():
+                self.sm_max = float(c[1]) if c[1].replace(".", "").isdigit() else None
+                self.rows.append((time.perf_counter(), float(c[0]), [x.lower().startswith("active") for x in c[3:7]]))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"]}
+        time.sleep(0.06)
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1] or list(self.rows)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None,
-                "reasons": reasons, "samples": len(rows)}
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in rows)]
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": getattr(self, "sm_max", None), "reasons": reasons,
+                "samples": len(rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def sample_cloud(n_total, n_sample, seed=0):
@@ -200,7 +238,8 @@ def main():
     launches = b200.launch_count() + 2 * args.steps               # + torch arange / cast per step (not ours, listed for honesty)
     own_launches = b200.launch_count()
     b200.profile_enable(False)
-    dev_ms = sum(s.elapsed_time(e) for s, e in ev)
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    dev_ms = sum(step_ms)
     tm = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -285,7 +324,8 @@ def main():
                            "eig_order": "literal"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": int(own_launches), "gpu_launches_per_step": own_launches / args.steps,
-                "wall_s_timed_region": t_wall1 - t_wall0}
+                "wall_s_timed_region": t_wall1 - t_wall0,
+                "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

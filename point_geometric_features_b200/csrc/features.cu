@@ -274,6 +274,101 @@ __global__ void __launch_bounds__(kRows) features_kernel(const FeatArgs a)
     store_rows<11>(a, t, s_out, s_rowid);
 }
 
+// compute_features, second layout: NO shared-memory tile for nn.  Every thread streams its own row of
+// nn straight from global memory with 64-bit loads (a row is a contiguous 4k-byte run; its 128-B
+// lines stay in L1 between the thread's visits) and keeps 8 independent 128-bit gathers in flight.
+// Without the 45 KB tile a CTA needs 6 KB of shared memory (output staging), so occupancy is bound by
+// registers only and the SM holds 3x more gathers in flight -- the kernel is bound by the latency of
+// random 32-B sector reads, not by issue slots.  HINT selects the gather's cache policy.
+template <int HINT>
+__device__ __forceinline__ float4 gather_point(const float4* p)
+{
+    float4 v;
+    if (HINT == 1)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else if (HINT == 2)
+        asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else
+        v = __ldg(p);
+    return v;
+}
+
+template <int HINT>
+__device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint32_t len, Moments& m)
+{
+    const uint32_t* __restrict__ p = a.nn + b;
+    const uint32_t n = a.n_xyz;
+    const uint32_t i0 = __ldg(p);
+    if (i0 >= n) return false;
+    const float4 o = gather_point<HINT>(a.xyz4 + i0);       // origin of the shifted moments; its own term is zero
+    bool ok = true;
+    uint32_t j = 1;
+    if (((b + j) & 1u) && j < len) {                         // align the stream to 8 bytes
+        uint32_t i = __ldg(p + j);
+        if (i >= n) { ok = false; i = i0; }
+        const float4 q = gather_point<HINT>(a.xyz4 + i);
+        m.add(q.x - o.x, q.y - o.y, q.z - o.z);
+        ++j;
+    }
+    for (; j + 8 <= len; j += 8) {
+        uint32_t i[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint2 w = __ldg(reinterpret_cast<const uint2*>(p + j) + u);
+            i[2 * u] = w.x; i[2 * u + 1] = w.y;
+        }
+        float4 q[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (i[u] >= n) { ok = false; i[u] = i0; }
+            q[u] = gather_point<HINT>(a.xyz4 + i[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
+    }
+    if (j < len) {                                           // up to 7 left: issue their gathers together as well
+        uint32_t i[7];
+        float4 q[7];
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            i[u] = j + u < len ? __ldg(p + j + u) : i0;
+            if (i[u] >= n) { ok = false; i[u] = i0; }
+        }
+#pragma unroll
+        for (int u = 0; u < 7; ++u) q[u] = gather_point<HINT>(a.xyz4 + i[u]);
+#pragma unroll
+        for (int u = 0; u < 7; ++u) if (j + u < len) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
+    }
+    return ok;
+}
+
+template <int HINT>
+__global__ void __launch_bounds__(kRows, 8) features_direct_kernel(const FeatArgs a)
+{
+    __shared__ uint32_t s_rowid[kRows];
+    __shared__ float s_out[kRows * 11];
+    const uint32_t r0 = blockIdx.x * kRows;
+    Tile t{r0, min((uint32_t)kRows, a.n_rows - r0), a.order == nullptr};
+    float f[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) f[i] = 0.f;
+    uint32_t row = r0 + threadIdx.x;
+    if (threadIdx.x < t.rows) {
+        if (a.order) row = __ldg(a.order + row);
+        const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+        if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
+        else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
+            Moments m;
+            if (!walk_direct<HINT>(a, b, e - b, m)) atomicExch(a.err, 2);
+            else features11<float>(m.pca(e - b, a.eig_order), f);
+        }
+    }
+    s_rowid[threadIdx.x] = row;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
+    store_rows<11>(a, t, s_out, s_rowid);
+}
+
 // ----------------------------------------------------------------------------------
 // compute_features_multiscale (pgeof.hpp:159-211): scale s uses the first k_s entries of
 // the row; one walk yields every scale from the running (prefix) moments.
@@ -374,10 +469,10 @@ __global__ void __launch_bounds__(256) pad_xyz_kernel(const float* __restrict__ 
     if (i < n) out[i] = make_float4(__ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2), 0.f);
 }
 
-struct RowGrid { float lo[3]; float scale[3]; int cells; };
+struct RowGrid { float lo[3]; float scale[3]; int cells; int morton; };
 
 // one warp: reduce the bbox partials and derive the coarse row-ordering grid (no host sync)
-__global__ void row_grid_kernel(const float* __restrict__ partial, int n_partial, int cells, RowGrid* __restrict__ g)
+__global__ void row_grid_kernel(const float* __restrict__ partial, int n_partial, int cells, int morton, RowGrid* __restrict__ g)
 {
     const int lane = threadIdx.x;
     float mn[3] = {3.4e38f, 3.4e38f, 3.4e38f}, mx[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
@@ -395,7 +490,18 @@ __global__ void row_grid_kernel(const float* __restrict__ partial, int n_partial
             g->scale[d] = (ext > 0.f && ext < 3.0e38f) ? (float)cells / ext : 0.f;
         }
         g->cells = cells;
+        g->morton = morton;
     }
+}
+
+// bits of a 10-bit value spread to every third position
+__device__ __forceinline__ uint32_t spread3(uint32_t v)
+{
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
 }
 
 __device__ __forceinline__ uint32_t row_key(const FeatArgs& a, const RowGrid& g, uint32_t row)
@@ -409,6 +515,10 @@ __device__ __forceinline__ uint32_t row_key(const FeatArgs& a, const RowGrid& g,
     const int cx = min(max(__float2int_rd((p.x - g.lo[0]) * g.scale[0]), 0), c - 1);
     const int cy = min(max(__float2int_rd((p.y - g.lo[1]) * g.scale[1]), 0), c - 1);
     const int cz = min(max(__float2int_rd((p.z - g.lo[2]) * g.scale[2]), 0), c - 1);
+    // Morton order of the coarse cells: rows that share neighbours are visited close in time along all three
+    // axes, so a gathered point is still in L2 when the next row needs it (a (z, y, x) raster order revisits the
+    // neighbouring plane only after a whole plane of rows: more gather traffic than the L2 holds)
+    if (g.morton) return spread3((uint32_t)cx) | (spread3((uint32_t)cy) << 1) | (spread3((uint32_t)cz) << 2);
     return ((uint32_t)cz * c + cy) * c + cx;
 }
 
@@ -493,14 +603,16 @@ int prepare(FeatArgs* a, Prepass* p, cudaStream_t stream)
     int n_partial = 0;
     PGEOF_TRY(bbox_partials(a->xyz, a->n_xyz, &partial, &n_partial, stream));
     int cells = (int)std::lround(std::cbrt((double)a->n_rows / 6.0));
-    cells = std::min(std::max(cells, 8), 160);
-    const size_t n_cells = (size_t)cells * cells * cells;
+    const int morton = env_int("PGEOF_FEATURES_MORTON", 1);
+    cells = std::min(std::max(cells, 8), morton ? 128 : 160);
+    size_t n_cells = (size_t)cells * cells * cells;
+    if (morton) { int bits = 3; while ((1 << bits) < cells) ++bits; n_cells = (size_t)1 << (3 * bits); }
     PGEOF_TRY(grid.alloc(sizeof(RowGrid), stream));
     PGEOF_TRY(counts.alloc((n_cells + 1) * sizeof(uint32_t), stream));
     PGEOF_TRY(keys.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     PGEOF_TRY(rank.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     PGEOF_TRY(p->order.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
-    row_grid_kernel<<<1, 32, 0, stream>>>(partial.as<float>(), n_partial, cells, grid.as<RowGrid>());
+    row_grid_kernel<<<1, 32, 0, stream>>>(partial.as<float>(), n_partial, cells, morton, grid.as<RowGrid>());
     PGEOF_LAUNCH_CHECK();
     PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, (n_cells + 1) * sizeof(uint32_t), stream));
     const unsigned blocks = (a->n_rows + 255) / 256;
@@ -550,9 +662,17 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
     a.k_min = k_min;
     Prepass pre;
     PGEOF_TRY(prepare(&a, &pre, stream));
-    const size_t fixed = Smem<11>::kNn;
-    a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
-    PGEOF_TRY(launch_tiles(features_kernel, "features", a, fixed + (size_t)a.nn_cap * 4, stream));
+    const int layout = env_int("PGEOF_FEATURES_LAYOUT", 1);   // 1: direct nn stream (default), 0: shared-memory nn tile
+    if (layout == 0) {
+        const size_t fixed = Smem<11>::kNn;
+        a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
+        PGEOF_TRY(launch_tiles(features_kernel, "features", a, fixed + (size_t)a.nn_cap * 4, stream));
+    } else {
+        const int hint = env_int("PGEOF_FEATURES_HINT", 0);
+        if (hint == 1) PGEOF_TRY(launch_tiles(features_direct_kernel<1>, "features", a, 0, stream));
+        else if (hint == 2) PGEOF_TRY(launch_tiles(features_direct_kernel<2>, "features", a, 0, stream));
+        else PGEOF_TRY(launch_tiles(features_direct_kernel<0>, "features", a, 0, stream));
+    }
     return device_flag_check(err.as<int>(), stream, "compute_features");
 }
 

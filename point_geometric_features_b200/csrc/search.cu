@@ -565,16 +565,21 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
             const uint32_t* plane_d = list;
             const uint32_t* plane_i = reinterpret_cast<const uint32_t*>(stage);
             const unsigned okm = __ballot_sync(kFull, ok);
-#pragma unroll 4
+            // branch free: predicated stores, one 64-bit row offset per row
+#pragma unroll 8
             for (int q = 0; q < 32; ++q) {
-                if (!((okm >> q) & 1u)) continue;
                 const uint32_t rowq = __shfl_sync(kFull, row, q);
-                uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)rowq * k;
-                float* d2 = a.sqr_dist + (size_t)rowq * k;
+                const size_t o = (size_t)rowq * k + lane;
+                uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + o;
+                float* d2 = a.sqr_dist + o;
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const uint32_t e = r * 32 + lane;
-                    if (e < k) { idx[e] = plane_i[e * S + q]; d2[e] = __uint_as_float(plane_d[e * S + q]); }
+                    const uint32_t vi = plane_i[e * S + q], vd = plane_d[e * S + q];
+                    const uint32_t on = (((okm >> q) & 1u) && e < k) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+                                 "@p st.global.u32 [%0], %2;\n\t@p st.global.u32 [%1], %3;\n\t}"
+                                 :: "l"(idx + r * 32), "l"(d2 + r * 32), "r"(vi), "r"(vd), "r"(on) : "memory");
                 }
             }
         }
