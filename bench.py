@@ -65,6 +65,8 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        if os.environ.get('PGEOF_BENCH_NO_CLOCKS'):
+            return
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -106,7 +108,7 @@ class ClockSampler:
                 self.rows.append((time.perf_counter(), sm, [bool(r & b) for b in bits]))
             except Exception:
                 pass
-            time.sleep(0.025)
+            time.sleep(float(os.environ.get('PGEOF_BENCH_CLOCK_PERIOD', '0.025')))
 
     def _read(self):
         for line in self.proc.stdout:
@@ -180,6 +182,10 @@ def main():
         run_reference(args, rank)
         return
 
+    # The drop-in API returns freshly allocated outputs (2 x 2 GB + 0.44 GB per step here), served by torch's caching
+    # allocator.  Left to split its 2 GB blocks for the 40-80 MB CSR glue tensors, it periodically has to cudaMalloc a
+    # new 2 GB block (80-500 ms, inside knn_search's host time); blocks above 256 MB are therefore never split.
+    os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "max_split_size_mb:256")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -205,11 +211,19 @@ def main():
     t = torch.from_numpy(xyz).to(dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    debug = bool(os.environ.get("PGEOF_BENCH_DEBUG"))
+    host_log = []
+
     def step():
+        h0 = time.perf_counter()
         q = t if (lo, hi) == (0, n) else t[lo:hi]
         idx, d2 = pgeof.knn_search(t, q, k)
+        h1 = time.perf_counter()
         nn_ptr = (torch.arange(hi - lo + 1, device=dev, dtype=torch.int64) * k).to(torch.uint32)
+        h2 = time.perf_counter()
         feats = pgeof.compute_features(t, idx.view(-1), nn_ptr)
+        if debug:
+            host_log.append((1e3 * (h1 - h0), 1e3 * (h2 - h1), 1e3 * (time.perf_counter() - h2)))
         return idx, d2, feats
 
     def barrier():
@@ -218,20 +232,25 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    out = None
     for _ in range(max(args.warmup, 3)):
-        step()
+        out = None                                                 # a caller's loop overwrites its previous results
+        out = step()
     barrier()
     b200.profile_reset()
-    b200.profile_enable(True)
+    b200.profile_enable(not os.environ.get('PGEOF_BENCH_NO_PROFILE'))
     b200.reset_launch_count()
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for s, e in ev:
+        out = None
         flush.zero_()                                              # L2 flush between timed iterations (not timed)
         s.record()
         out = step()
         e.record()
+        torch.cuda.synchronize()                                   # outside the step's event pair, like the flush: keeps the host from
+                                                                   # racing ahead into the next step's allocations (measured: removes 2-500 ms host stalls)
     barrier()
     t_wall1 = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_wall1)
@@ -239,6 +258,10 @@ def main():
     own_launches = b200.launch_count()
     b200.profile_enable(False)
     step_ms = [s.elapsed_time(e) for s, e in ev]
+    if debug and rank == 0:
+        for i, ms in enumerate(step_ms):
+            h = host_log[len(host_log) - len(step_ms) + i]
+            print("step %d dev %.2f ms | host knn %.2f glue %.2f feat %.2f" % (i, ms, h[0], h[1], h[2]), file=sys.stderr)
     dev_ms = sum(step_ms)
     tm = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
