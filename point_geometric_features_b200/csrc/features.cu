@@ -49,6 +49,7 @@ struct FeatArgs {
     int* err;
     uint32_t nn_cap;       // entries of `nn` the shared-memory tile can hold
     int tma_in, tma_out;   // pointer alignment allows bulk copies
+    int out_by_position;   // direct kernel: `out` is indexed by position in the row sequence (un-permuted by a second pass)
     // multiscale
     uint32_t scales[kMaxScalesPerPass]; uint32_t n_scales_pass; uint32_t n_scales_total; uint32_t scale_base;
     // optimal
@@ -280,17 +281,43 @@ __global__ void __launch_bounds__(kRows) features_kernel(const FeatArgs a)
 // Without the 45 KB tile a CTA needs 6 KB of shared memory (output staging), so occupancy is bound by
 // registers only and the SM holds 3x more gathers in flight -- the kernel is bound by the latency of
 // random 32-B sector reads, not by issue slots.  HINT selects the gather's cache policy.
+// L2 eviction policies: the gathered cloud is re-used ~k times while the rows around a point are processed,
+// nn and the outputs stream through once; without hints the stream evicts the cloud (29 % of the gathers missed L2)
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
 template <int HINT>
-__device__ __forceinline__ float4 gather_point(const float4* p)
+__device__ __forceinline__ float4 gather_point(const float4* p, uint64_t pol)
 {
     float4 v;
     if (HINT == 1)
         asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     else if (HINT == 2)
         asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else if (HINT >= 3)
+        asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
     else
         v = __ldg(p);
     return v;
+}
+
+template <int HINT>
+__device__ __forceinline__ uint2 stream_nn2(const uint32_t* p, uint64_t pol)
+{
+    uint2 w;
+    if (HINT == 4) asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(w.x), "=r"(w.y) : "l"(p), "l"(pol));
+    else w = __ldg(reinterpret_cast<const uint2*>(p));
+    return w;
 }
 
 template <int HINT>
@@ -300,13 +327,14 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
     const uint32_t n = a.n_xyz;
     const uint32_t i0 = __ldg(p);
     if (i0 >= n) return false;
-    const float4 o = gather_point<HINT>(a.xyz4 + i0);       // origin of the shifted moments; its own term is zero
+    const uint64_t pol_keep = HINT >= 3 ? l2_policy_evict_last() : 0, pol_stream = HINT == 4 ? l2_policy_evict_first() : 0;
+    const float4 o = gather_point<HINT>(a.xyz4 + i0, pol_keep);   // origin of the shifted moments; its own term is zero
     bool ok = true;
     uint32_t j = 1;
     if (((b + j) & 1u) && j < len) {                         // align the stream to 8 bytes
         uint32_t i = __ldg(p + j);
         if (i >= n) { ok = false; i = i0; }
-        const float4 q = gather_point<HINT>(a.xyz4 + i);
+        const float4 q = gather_point<HINT>(a.xyz4 + i, pol_keep);
         m.add(q.x - o.x, q.y - o.y, q.z - o.z);
         ++j;
     }
@@ -314,14 +342,14 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
         uint32_t i[8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const uint2 w = __ldg(reinterpret_cast<const uint2*>(p + j) + u);
+            const uint2 w = stream_nn2<HINT>(p + j + 2 * u, pol_stream);
             i[2 * u] = w.x; i[2 * u + 1] = w.y;
         }
         float4 q[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             if (i[u] >= n) { ok = false; i[u] = i0; }
-            q[u] = gather_point<HINT>(a.xyz4 + i[u]);
+            q[u] = gather_point<HINT>(a.xyz4 + i[u], pol_keep);
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
@@ -335,7 +363,7 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
             if (i[u] >= n) { ok = false; i[u] = i0; }
         }
 #pragma unroll
-        for (int u = 0; u < 7; ++u) q[u] = gather_point<HINT>(a.xyz4 + i[u]);
+        for (int u = 0; u < 7; ++u) q[u] = gather_point<HINT>(a.xyz4 + i[u], pol_keep);
 #pragma unroll
         for (int u = 0; u < 7; ++u) if (j + u < len) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
     }
@@ -348,13 +376,15 @@ __global__ void __launch_bounds__(kRows, 8) features_direct_kernel(const FeatArg
     __shared__ uint32_t s_rowid[kRows];
     __shared__ float s_out[kRows * 11];
     const uint32_t r0 = blockIdx.x * kRows;
-    Tile t{r0, min((uint32_t)kRows, a.n_rows - r0), a.order == nullptr};
+    // out_by_position: a.out is indexed by POSITION in the (permuted) row sequence, the tile's output is one contiguous block
+    Tile t{r0, min((uint32_t)kRows, a.n_rows - r0), a.order == nullptr || a.out_by_position != 0};
     float f[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) f[i] = 0.f;
     uint32_t row = r0 + threadIdx.x;
+    if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
+    s_rowid[threadIdx.x] = a.out_by_position ? r0 + threadIdx.x : row;
     if (threadIdx.x < t.rows) {
-        if (a.order) row = __ldg(a.order + row);
         const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
         if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
         else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
@@ -363,10 +393,28 @@ __global__ void __launch_bounds__(kRows, 8) features_direct_kernel(const FeatArg
             else features11<float>(m.pca(e - b, a.eig_order), f);
         }
     }
-    s_rowid[threadIdx.x] = row;
 #pragma unroll
     for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
     store_rows<11>(a, t, s_out, s_rowid);
+}
+
+// out[row] = tmp[inv[row]]: undoes the spatial row permutation with random 4F-byte READS and fully coalesced
+// writes (scattered 44-B row writes from the feature kernel cost more than the whole neighbourhood walk:
+// partial-sector writes, profiles/r1f)
+template <int F>
+__global__ void __launch_bounds__(kRows) unpermute_kernel(const float* __restrict__ tmp, const uint32_t* __restrict__ inv, uint32_t n_rows,
+                                                          float* __restrict__ out)
+{
+    __shared__ float s[kRows * F];
+    const uint32_t r0 = blockIdx.x * kRows;
+    const uint32_t rows = min((uint32_t)kRows, n_rows - r0);
+    if (threadIdx.x < rows) {
+        const float* src = tmp + (size_t)__ldg(inv + r0 + threadIdx.x) * F;
+#pragma unroll
+        for (int f = 0; f < F; ++f) s[threadIdx.x * F + f] = __ldg(src + f);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < rows * F; i += kRows) out[(size_t)r0 * F + i] = s[i];
 }
 
 // ----------------------------------------------------------------------------------
@@ -545,10 +593,15 @@ __global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const 
 }
 
 __global__ void __launch_bounds__(256) row_scatter_kernel(uint32_t n_rows, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ keys,
-                                                          const uint32_t* __restrict__ rank, uint32_t* __restrict__ order)
+                                                          const uint32_t* __restrict__ rank, uint32_t* __restrict__ order,
+                                                          uint32_t* __restrict__ inverse)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_rows) order[__ldg(starts + keys[i]) + rank[i]] = i;
+    if (i < n_rows) {
+        const uint32_t pos = __ldg(starts + keys[i]) + rank[i];
+        order[pos] = i;
+        inverse[i] = pos;
+    }
 }
 
 // shared-memory tile for `nn`: mean row length with 50 % head-room, at least 32 entries a row
@@ -577,7 +630,7 @@ int make_args(FeatArgs* a, const float* xyz, size_t n_xyz, const uint32_t* nn, s
 // Device buffers of the two pre-passes; they live until the feature kernel was enqueued
 // (stream-ordered frees).
 struct Prepass {
-    DeviceBuffer xyz4, order;
+    DeviceBuffer xyz4, order, inverse;
 };
 
 int env_int(const char* name, int dflt)
@@ -612,6 +665,7 @@ int prepare(FeatArgs* a, Prepass* p, cudaStream_t stream)
     PGEOF_TRY(keys.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     PGEOF_TRY(rank.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     PGEOF_TRY(p->order.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
+    PGEOF_TRY(p->inverse.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     row_grid_kernel<<<1, 32, 0, stream>>>(partial.as<float>(), n_partial, cells, morton, grid.as<RowGrid>());
     PGEOF_LAUNCH_CHECK();
     PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, (n_cells + 1) * sizeof(uint32_t), stream));
@@ -619,7 +673,7 @@ int prepare(FeatArgs* a, Prepass* p, cudaStream_t stream)
     row_count_kernel<<<blocks, 256, 0, stream>>>(*a, grid.as<RowGrid>(), counts.as<uint32_t>(), keys.as<uint32_t>(), rank.as<uint32_t>());
     PGEOF_LAUNCH_CHECK();
     PGEOF_TRY(exclusive_scan_u32(counts.as<uint32_t>(), n_cells, stream));
-    row_scatter_kernel<<<blocks, 256, 0, stream>>>(a->n_rows, counts.as<uint32_t>(), keys.as<uint32_t>(), rank.as<uint32_t>(), p->order.as<uint32_t>());
+    row_scatter_kernel<<<blocks, 256, 0, stream>>>(a->n_rows, counts.as<uint32_t>(), keys.as<uint32_t>(), rank.as<uint32_t>(), p->order.as<uint32_t>(), p->inverse.as<uint32_t>());
     PGEOF_LAUNCH_CHECK();
     a->order = p->order.as<uint32_t>();
     return PGEOF_OK;
@@ -668,10 +722,26 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
         a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
         PGEOF_TRY(launch_tiles(features_kernel, "features", a, fixed + (size_t)a.nn_cap * 4, stream));
     } else {
+        // permuted rows: features land in a position-indexed scratch block, then one gather pass restores row order
+        DeviceBuffer tmp;
+        const bool unpermute = a.order && env_int("PGEOF_FEATURES_UNPERMUTE", 0) != 0;   // measured: no gain over scattered row writes
+        if (unpermute) {
+            a.out_by_position = 1;
+            PGEOF_TRY(tmp.alloc(n_rows * 11 * sizeof(float), stream));
+            a.out = tmp.as<float>();
+            a.tma_out = 1;
+        }
         const int hint = env_int("PGEOF_FEATURES_HINT", 0);
         if (hint == 1) PGEOF_TRY(launch_tiles(features_direct_kernel<1>, "features", a, 0, stream));
         else if (hint == 2) PGEOF_TRY(launch_tiles(features_direct_kernel<2>, "features", a, 0, stream));
+        else if (hint == 3) PGEOF_TRY(launch_tiles(features_direct_kernel<3>, "features", a, 0, stream));
+        else if (hint == 4) PGEOF_TRY(launch_tiles(features_direct_kernel<4>, "features", a, 0, stream));
         else PGEOF_TRY(launch_tiles(features_direct_kernel<0>, "features", a, 0, stream));
+        if (unpermute) {
+            KernelTimer timer("row_order", stream);
+            unpermute_kernel<11><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(tmp.as<float>(), pre.inverse.as<uint32_t>(), (uint32_t)n_rows, out);
+            PGEOF_LAUNCH_CHECK();
+        }
     }
     return device_flag_check(err.as<int>(), stream, "compute_features");
 }

@@ -12,7 +12,9 @@
 //    bulk copy per cell row.  Every candidate is read ONCE per warp (a warp-uniform 128-bit
 //    load) and tested by the 32 lanes against their own query -- no ballots, shuffles or partially
 //    filled 32-candidate chunks in the inner loop.  Survivors (d2 <= fl(0.9999 R^2)) are appended
-//    to a per-lane shared-memory list as 32-bit words (22 bits of d2 | staged slot).  Each lane
+//    to a per-lane shared-memory list as 32-bit words (22 bits of d2 | staged slot); the scan uses the
+//    FMA-contracted distance (6 instead of 8 FP32 instructions per candidate), every distance that is
+//    returned or decides an order is recomputed with the defined, non-contracted formula.  Each lane
 //    then loads its list into registers and runs a min/max sorting network that leaves the 64
 //    smallest of up to 96 (128) words in order; the exact (d2, index) pairs are rebuilt from the
 //    staged candidates in that order, rows whose truncated keys collided are repaired by an
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         // ---- scan: every candidate is read once per warp (broadcast) and tested by all lanes ------
         // accept iff d2 <= t2 with t2 strictly inside R^2, so every accepted point is in the region
         const float t2 = mine ? __fmul_rd(__fmul_rd(R, R), 0.9999f) : -1.f;
+        const float t2_safe = __fmul_rd(t2, 0.99999618530273f);   // t2 (1 - 2^-18)
         uint32_t* const wbase = list + lane;
         // shared-memory byte address of the lane's next free entry: advances by one stride per survivor;
         // clamped once per batch of 8 to entry NLOAD + 1 (so the count saturates at NLOAD + 1 = overflow)
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         for (uint32_t c = 0; c < C8; c += 8) {
             float d[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float4 p = stage[c + i]; d[i] = sqdist_f32(qx, qy, qz, p.x, p.y, p.z); }
+            for (int i = 0; i < 8; ++i) { const float4 p = stage[c + i]; d[i] = sqdist_fused(qx, qy, qz, p.x, p.y, p.z); }
 #pragma unroll
             for (int i = 0; i < 8; ++i) PGEOF_TILE_APPEND(d[i], c + i)
             waddr = min(waddr, wclamp);
@@ -520,33 +523,20 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
         {
             uint32_t* plane_d = list + lane;
             uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
-            // a dropped key that shares the truncated distance of the k-th neighbour may belong before it
-            const bool tie = ok && dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) == (plane_d[(k - 1) * S] >> Cfg::SLOT_BITS);
-            if (tie) ok = false;
-            if (a.stats) {
-                const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && (bad[0] | bad[M - 1]));
-                if (lane == 0) {
-                    atomicAdd(a.stats + ST_TIE, (unsigned long long)__popc(tm));
-                    atomicAdd(a.stats + ST_FIXED, (unsigned long long)__popc(fm));
-                }
-            }
             uint32_t any_bad = 0;
 #pragma unroll
             for (int r = 0; r < M; ++r) any_bad |= bad[r];
             if (ok && any_bad) {
-                // insertion sort on the exact (d2, index) order, from the first inversion to the end of the tie
-                // group (equal truncated distance) that holds the last one: everything else is in order already
+                // insertion sort on the exact (d2, index) order from the first inversion on; past the last
+                // inversion the first entry found in place ends it (everything behind it is in order already)
                 uint32_t first = 0, last = 0;
 #pragma unroll
                 for (int r = M - 1; r >= 0; --r) if (bad[r]) first = r * 32 + __ffs(bad[r]) - 1;
 #pragma unroll
                 for (int r = 0; r < M; ++r) if (bad[r]) last = r * 32 + 31 - __clz(bad[r]);
                 const uint32_t nfix = min(cnt, (uint32_t)NOUT);
-                uint32_t pt = 0;
                 for (uint32_t i = first; i < nfix; ++i) {
                     const uint32_t d = plane_d[i * S], id = plane_i[i * S];
-                    if (i > last && (d >> Cfg::SLOT_BITS) != pt) break;
-                    pt = d >> Cfg::SLOT_BITS;
                     uint32_t j = i;
                     while (j > 0) {
                         const uint32_t qd = plane_d[(j - 1) * S], qi = plane_i[(j - 1) * S];
@@ -555,6 +545,22 @@ __global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_ke
                         --j;
                     }
                     if (j != i) { plane_d[j * S] = d; plane_i[j * S] = id; }
+                    else if (i > last) break;
+                }
+            }
+            // The scan ordered and accepted candidates by the FUSED distance, which is within 2^-21 (relative) of
+            // the defined one: at most one truncation bucket (2^-13) off.  The row is exact iff
+            //  (a) no dropped key can precede the k-th neighbour: bucket(dropped) >= bucket(k-th) + 2, and
+            //  (b) no rejected candidate can: d2(k-th) <= t2 (1 - 2^-18) < defined d2 of anything rejected.
+            const uint32_t kth = plane_d[(k - 1) * S];
+            const bool tie = ok && ((dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u) ||
+                                    !(__uint_as_float(kth) <= t2_safe));
+            if (tie) ok = false;
+            if (a.stats) {
+                const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && any_bad);
+                if (lane == 0) {
+                    atomicAdd(a.stats + ST_TIE, (unsigned long long)__popc(tm));
+                    atomicAdd(a.stats + ST_FIXED, (unsigned long long)__popc(fm));
                 }
             }
         }

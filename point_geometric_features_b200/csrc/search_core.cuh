@@ -22,6 +22,13 @@ __device__ __forceinline__ float sqdist_f32(float qx, float qy, float qz, float 
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// FMA-contracted variant for filtering only (within 2^-21 relative of sqdist_f32; never returned to the caller)
+__device__ __forceinline__ float sqdist_fused(float qx, float qy, float qz, float px, float py, float pz)
+{
+    const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
 __device__ __forceinline__ u64 make_key(float d2, uint32_t idx) { return ((u64)__float_as_uint(d2) << 32) | idx; }
 __device__ __forceinline__ float key_d2(u64 k) { return __uint_as_float((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_idx(u64 k) { return (uint32_t)k; }
