@@ -198,7 +198,7 @@ __device__ __forceinline__ void store_rows(const FeatArgs& a, const Tile& t, con
             ptx::bulk_wait_read0();
         }
     } else {
-        for (uint32_t i = threadIdx.x; i < total; i += kRows) {
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
             const uint32_t r = i / F, f = i - r * F;
             a.out[(size_t)s_rowid[r] * F + f] = s_out[i];
         }
@@ -311,13 +311,32 @@ __device__ __forceinline__ float4 gather_point(const float4* p, uint64_t pol)
     return v;
 }
 
+// eight consecutive entries of nn with ONE 256-bit load that does not allocate in L1 (sm_100 LDG.256): the stream
+// is read exactly once, and 1024 resident rows x one 128-B line each would otherwise crowd the gathered
+// points out of L1.  p must be 32-byte aligned.
 template <int HINT>
-__device__ __forceinline__ uint2 stream_nn2(const uint32_t* p, uint64_t pol)
+__device__ __forceinline__ void stream_nn8(const uint32_t* p, uint32_t (&i)[8])
 {
-    uint2 w;
-    if (HINT == 4) asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(w.x), "=r"(w.y) : "l"(p), "l"(pol));
-    else w = __ldg(reinterpret_cast<const uint2*>(p));
-    return w;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(i[0]), "=r"(i[1]), "=r"(i[2]), "=r"(i[3]), "=r"(i[4]), "=r"(i[5]), "=r"(i[6]), "=r"(i[7]) : "l"(p));
+}
+
+// up to N (<= 7) consecutive entries: indices first, then their gathers together, then the moments in order
+template <int HINT, int N>
+__device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __restrict__ p, uint32_t cnt, uint32_t i0, const float4& o,
+                                          uint64_t pol_keep, Moments& m, bool& ok)
+{
+    uint32_t i[N];
+    float4 q[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        i[u] = (uint32_t)u < cnt ? __ldg(p + u) : i0;
+        if (i[u] >= a.n_xyz) { ok = false; i[u] = i0; }
+    }
+#pragma unroll
+    for (int u = 0; u < N; ++u) q[u] = gather_point<HINT>(a.xyz4 + i[u], pol_keep);
+#pragma unroll
+    for (int u = 0; u < N; ++u) if ((uint32_t)u < cnt) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
 }
 
 template <int HINT>
@@ -327,24 +346,16 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
     const uint32_t n = a.n_xyz;
     const uint32_t i0 = __ldg(p);
     if (i0 >= n) return false;
-    const uint64_t pol_keep = HINT >= 3 ? l2_policy_evict_last() : 0, pol_stream = HINT == 4 ? l2_policy_evict_first() : 0;
+    const uint64_t pol_keep = HINT >= 3 ? l2_policy_evict_last() : 0;
     const float4 o = gather_point<HINT>(a.xyz4 + i0, pol_keep);   // origin of the shifted moments; its own term is zero
     bool ok = true;
     uint32_t j = 1;
-    if (((b + j) & 1u) && j < len) {                         // align the stream to 8 bytes
-        uint32_t i = __ldg(p + j);
-        if (i >= n) { ok = false; i = i0; }
-        const float4 q = gather_point<HINT>(a.xyz4 + i, pol_keep);
-        m.add(q.x - o.x, q.y - o.y, q.z - o.z);
-        ++j;
-    }
+    // head: up to the next 32-byte boundary of the stream (whatever the alignment of nn itself)
+    const uint32_t nh = min((uint32_t)((0u - (uint32_t)reinterpret_cast<uintptr_t>(p + 1)) & 31u) >> 2, len - 1u);
+    if (nh) { walk_some<HINT, 7>(a, p + j, nh, i0, o, pol_keep, m, ok); j += nh; }
     for (; j + 8 <= len; j += 8) {
         uint32_t i[8];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const uint2 w = stream_nn2<HINT>(p + j + 2 * u, pol_stream);
-            i[2 * u] = w.x; i[2 * u + 1] = w.y;
-        }
+        stream_nn8<HINT>(p + j, i);
         float4 q[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -354,48 +365,46 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
 #pragma unroll
         for (int u = 0; u < 8; ++u) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
     }
-    if (j < len) {                                           // up to 7 left: issue their gathers together as well
-        uint32_t i[7];
-        float4 q[7];
-#pragma unroll
-        for (int u = 0; u < 7; ++u) {
-            i[u] = j + u < len ? __ldg(p + j + u) : i0;
-            if (i[u] >= n) { ok = false; i[u] = i0; }
-        }
-#pragma unroll
-        for (int u = 0; u < 7; ++u) q[u] = gather_point<HINT>(a.xyz4 + i[u], pol_keep);
-#pragma unroll
-        for (int u = 0; u < 7; ++u) if (j + u < len) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
-    }
+    if (j < len) walk_some<HINT, 7>(a, p + j, len - j, i0, o, pol_keep, m, ok);
     return ok;
 }
 
-template <int HINT>
-__global__ void __launch_bounds__(kRows, 8) features_direct_kernel(const FeatArgs a)
+// THREADS rows per tile, one thread per row.  Every CTA owns a CONTIGUOUS chunk of the (spatially ordered) row
+// sequence and walks it tile by tile: the rows an SM works on at any time form one or two compact blobs, so a
+// gathered point is re-used out of L1 by the blob's other rows (small independent CTAs spread over the whole
+// in-flight window shared their gathers only through L2).
+template <int HINT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kernel(const FeatArgs a)
 {
-    __shared__ uint32_t s_rowid[kRows];
-    __shared__ float s_out[kRows * 11];
-    const uint32_t r0 = blockIdx.x * kRows;
-    // out_by_position: a.out is indexed by POSITION in the (permuted) row sequence, the tile's output is one contiguous block
-    Tile t{r0, min((uint32_t)kRows, a.n_rows - r0), a.order == nullptr || a.out_by_position != 0};
-    float f[11];
+    __shared__ uint32_t s_rowid[THREADS];
+    __shared__ float s_out[THREADS * 11];
+    const uint32_t tiles = (a.n_rows + THREADS - 1) / THREADS;
+    const uint32_t per = (tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_end = min(tiles, (blockIdx.x + 1) * per);
+    for (uint32_t tile = blockIdx.x * per; tile < t_end; ++tile) {
+        const uint32_t r0 = tile * THREADS;
+        // out_by_position: a.out is indexed by POSITION in the (permuted) row sequence, the tile's output is one contiguous block
+        Tile t{r0, min((uint32_t)THREADS, a.n_rows - r0), a.order == nullptr || a.out_by_position != 0};
+        float f[11];
 #pragma unroll
-    for (int i = 0; i < 11; ++i) f[i] = 0.f;
-    uint32_t row = r0 + threadIdx.x;
-    if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
-    s_rowid[threadIdx.x] = a.out_by_position ? r0 + threadIdx.x : row;
-    if (threadIdx.x < t.rows) {
-        const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
-        if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
-        else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
-            Moments m;
-            if (!walk_direct<HINT>(a, b, e - b, m)) atomicExch(a.err, 2);
-            else features11<float>(m.pca(e - b, a.eig_order), f);
+        for (int i = 0; i < 11; ++i) f[i] = 0.f;
+        uint32_t row = r0 + threadIdx.x;
+        if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
+        s_rowid[threadIdx.x] = a.out_by_position ? r0 + threadIdx.x : row;
+        if (threadIdx.x < t.rows) {
+            const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+            if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
+            else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
+                Moments m;
+                if (!walk_direct<HINT>(a, b, e - b, m)) atomicExch(a.err, 2);
+                else features11<float>(m.pca(e - b, a.eig_order), f);
+            }
         }
-    }
 #pragma unroll
-    for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
-    store_rows<11>(a, t, s_out, s_rowid);
+        for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
+        store_rows<11>(a, t, s_out, s_rowid);
+        __syncthreads();                                         // the staging buffers are re-used by the next tile
+    }
 }
 
 // out[row] = tmp[inv[row]]: undoes the spatial row permutation with random 4F-byte READS and fully coalesced
@@ -732,11 +741,26 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
             a.tma_out = 1;
         }
         const int hint = env_int("PGEOF_FEATURES_HINT", 0);
-        if (hint == 1) PGEOF_TRY(launch_tiles(features_direct_kernel<1>, "features", a, 0, stream));
-        else if (hint == 2) PGEOF_TRY(launch_tiles(features_direct_kernel<2>, "features", a, 0, stream));
-        else if (hint == 3) PGEOF_TRY(launch_tiles(features_direct_kernel<3>, "features", a, 0, stream));
-        else if (hint == 4) PGEOF_TRY(launch_tiles(features_direct_kernel<4>, "features", a, 0, stream));
-        else PGEOF_TRY(launch_tiles(features_direct_kernel<0>, "features", a, 0, stream));
+        const int cta = env_int("PGEOF_FEATURES_CTA", 512);
+        int dev = 0, sms = 148;
+        PGEOF_CUDA(cudaGetDevice(&dev));
+        PGEOF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        auto launch = [&](auto kern, int threads) -> int {
+            const unsigned tiles = (unsigned)((n_rows + threads - 1) / threads);
+            const unsigned blocks = std::min<unsigned>(tiles, (unsigned)(sms * (1024 / threads) * env_int("PGEOF_FEATURES_WAVES", 1 << 20)));
+            {
+                KernelTimer timer("features", stream);
+                kern<<<blocks, threads, 0, stream>>>(a);
+            }
+            PGEOF_LAUNCH_CHECK();
+            return PGEOF_OK;
+        };
+        a.tma_out = a.tma_out && ((cta * 11 * 4) % 16 == 0);
+        if (hint == 4 && cta == 512) PGEOF_TRY(launch(features_direct_kernel<4, 512>, 512));
+        else if (cta == 128) PGEOF_TRY(launch(features_direct_kernel<0, 128>, 128));
+        else if (cta == 256) PGEOF_TRY(launch(features_direct_kernel<0, 256>, 256));
+        else if (cta == 1024) PGEOF_TRY(launch(features_direct_kernel<0, 1024>, 1024));
+        else PGEOF_TRY(launch(features_direct_kernel<0, 512>, 512));
         if (unpermute) {
             KernelTimer timer("row_order", stream);
             unpermute_kernel<11><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(tmp.as<float>(), pre.inverse.as<uint32_t>(), (uint32_t)n_rows, out);

@@ -263,13 +263,13 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
 // one thread per query, one warp per 32 cell-sorted queries: kNN with k <= 64
 // ---------------------------------------------------------------------------------------
 // NOUT = sorted outputs kept per query (>= k), NEXTRA = further survivors the network can absorb.
-template <int NOUT, int NEXTRA>
+template <int NOUT, int NEXTRA, int NWARPS = 2>
 struct TileCfg {
     static constexpr int NLOAD = NOUT + NEXTRA;    // survivors a lane can sort
     static constexpr int SINK = 11;                // a batch of 8 appends may run 8 entries past the clamp (11: 16-B multiple)
     static constexpr int LCAP = NLOAD + 1 + SINK;  // list entries per lane
     static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
-    static constexpr int WARPS = 2;
+    static constexpr int WARPS = NWARPS;
     static constexpr int CMAX = NLOAD <= 96 ? 896 : 832;   // candidates staged per pass (16 B each), multiple of 8
     static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
     static constexpr int STAGE_BYTES = CMAX * 16;
@@ -311,10 +311,10 @@ __device__ __forceinline__ uint32_t select_sort_network(uint32_t (&v)[NOUT + NEX
     return dropped;
 }
 
-template <int NOUT, int NEXTRA>
-__global__ void __launch_bounds__(TileCfg<NOUT, NEXTRA>::WARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
+template <int NOUT, int NEXTRA, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
 {
-    using Cfg = TileCfg<NOUT, NEXTRA>;
+    using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     constexpr int M = NOUT / 32, NLOAD = Cfg::NLOAD, S = Cfg::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_tile[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -640,12 +640,12 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
-template <int NOUT, int NEXTRA>
+template <int NOUT, int NEXTRA, int NWARPS = 2>
 int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
-    using Cfg = TileCfg<NOUT, NEXTRA>;
+    using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
-    auto kern = knn_tile_kernel<NOUT, NEXTRA>;
+    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS>;
     PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
     {
@@ -721,7 +721,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         }
         int st;
         if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
-        else if (k <= 52) st = launch_tile<64, 32>(grid.view, a, stream);
+        else if (k <= 52) st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
         else st = launch_tile<64, 64>(grid.view, a, stream);
         if (st == PGEOF_OK && want_stats) {
             unsigned long long h[ST_N];
