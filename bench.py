@@ -296,8 +296,8 @@ def main():
 
         def host_step():
             knn, _d2 = pgeof.knn_search(hx, hq, k)                  # numpy in -> numpy out (H2D + D2H inside)
-            nn_ptr = (np.arange(hi - lo + 1, dtype=np.uint64) * k).astype(np.uint32)
-            nn = knn.reshape(-1)                                    # README glue, zero-copy
+            nn_ptr = np.arange(0, (hi - lo + 1) * k, k, dtype=np.uint32)   # README glue (README.md:135-141) in one numpy pass
+            nn = knn.reshape(-1)                                    # zero-copy: knn is already uint32
             f = pgeof.compute_features(hx, nn, nn_ptr)
             return float(f[0, 0])                                   # read the result on the host
 
