@@ -216,10 +216,13 @@ def main():
 
     def step():
         h0 = time.perf_counter()
-        q = t if (lo, hi) == (0, n) else t[lo:hi]
+        if world == 1 or weak:
+            q = t
+        else:                                                      # this rank's slab of the replicated cloud (no collective)
+            q = t[shard.spatial_shard(t, rank, world)]
         idx, d2 = pgeof.knn_search(t, q, k)
         h1 = time.perf_counter()
-        nn_ptr = (torch.arange(hi - lo + 1, device=dev, dtype=torch.int64) * k).to(torch.uint32)
+        nn_ptr = (torch.arange(q.shape[0] + 1, device=dev, dtype=torch.int64) * k).to(torch.uint32)
         h2 = time.perf_counter()
         feats = pgeof.compute_features(t, idx.view(-1), nn_ptr)
         if debug:
@@ -272,11 +275,9 @@ def main():
     for name in ("knn_search", "features", "grid_build"):
         ms, cnt = b200.profile_read(name)
         kernels[name] = {"ms_per_launch": ms / max(cnt, 1), "launches": int(cnt)}
-    del out
-
     # ---- roofline of the dominant kernel (algorithmic bytes of SURVEY.md 8d) --------------------
     peak, peak_src = peaks()
-    rows = hi - lo
+    rows = int(out[0].shape[0]) if out is not None else hi - lo
     alg = {"knn_search": (24 + 8 * k) * rows, "features": (48 + 16 * k) * rows}
     dom = max(("knn_search", "features"), key=lambda nme: kernels[nme]["ms_per_launch"])
     ach = alg[dom] / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
@@ -286,6 +287,10 @@ def main():
                 "all_kernels": {nme: {"ms": kernels[nme]["ms_per_launch"],
                                       "achieved_gbs": (alg[nme] / (kernels[nme]["ms_per_launch"] * 1e-3) / 1e9) if nme in alg and kernels[nme]["ms_per_launch"] > 0 else None}
                                 for nme in kernels}}
+
+    rows_dev = rows
+    del out
+    rows = hi - lo
 
     # ---- end to end through the drop-in module with host buffers --------------------------------
     e2e = None
@@ -342,7 +347,8 @@ def main():
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "uniform [0,200)^3 float32 cloud (seed 0), knn_search(k=%d) -> CSR view -> compute_features (11 features); grid build included in every step" % k,
-                           "points": n_total, "knn": k, "rows_per_rank": rows, "parallelism": "query-sharded x%d, cloud replicated, no data-path collective" % world,
+                           "points": n_total, "knn": k, "rows_per_rank": rows_dev,
+                           "parallelism": "query-sharded x%d (z slabs of ~n/N points from histogram quantiles, computed inside the step), cloud and grid replicated, no data-path collective; e2e shards by contiguous row range" % world,
                            "l2": "512 MiB buffer zeroed between timed iterations; per-step working set %.1f GB >> 126 MB L2" % ((rows * (k * 12 + 44) + n * 28) / 1e9),
                            "eig_order": "literal"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,

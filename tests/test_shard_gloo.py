@@ -40,9 +40,16 @@ def _worker(rank, world, port, n, k, out_dir):
     feats = cpu.compute_features(xyz, idx.reshape(-1), nn_ptr, 1, f64=False)
     full = shard.gather_rows(torch.from_numpy(feats), n, dist)
     full_idx = shard.gather_rows(torch.from_numpy(idx.astype(np.int64)), n, dist)
+    # spatial shards (z slabs): same pipeline on the rows spatial_shard hands this rank
+    rows = shard.spatial_shard(torch.from_numpy(xyz), rank, world)
+    sidx, _ = cpu.knn_search(xyz, xyz[rows.numpy()], k)
+    sptr = shard.local_knn_csr(rows.shape[0], k, torch, "cpu").numpy()
+    sfeats = cpu.compute_features(xyz, sidx.reshape(-1), sptr, 1, f64=False)
+    sfull = shard.gather_rows_indexed(torch.from_numpy(sfeats), rows, n, dist)
     if rank == 0:
         np.save(os.path.join(out_dir, "feats.npy"), full.numpy())
         np.save(os.path.join(out_dir, "idx.npy"), full_idx.numpy())
+        np.save(os.path.join(out_dir, "feats_spatial.npy"), sfull.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,3 +68,16 @@ def test_two_rank_shards_reassemble_to_single_process_result(tmp_path):
     ref = cpu.compute_features(xyz, idx.reshape(-1), nn_ptr, 1, f64=False)
     np.testing.assert_array_equal(np.load(tmp_path / "idx.npy"), idx.astype(np.int64))
     np.testing.assert_array_equal(np.load(tmp_path / "feats.npy"), ref)
+    np.testing.assert_array_equal(np.load(tmp_path / "feats_spatial.npy"), ref)
+
+
+def test_spatial_shards_partition_the_rows():
+    import torch
+    x = torch.from_numpy(np.random.default_rng(1).normal(0, 30, (20011, 3)).astype(np.float32))
+    for world in (1, 2, 3, 8):
+        sels = [shard.spatial_shard(x, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(sels).sort().values, torch.arange(x.shape[0]))
+        sizes = [int(s.shape[0]) for s in sels]
+        assert max(sizes) - min(sizes) <= 0.01 * x.shape[0] / world + 8           # balanced up to the histogram resolution
+        for r in range(world - 1):                                              # slabs are ordered along z
+            assert x[sels[r], 2].max() <= x[sels[r + 1], 2].min()
