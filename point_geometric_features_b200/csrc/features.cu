@@ -322,9 +322,9 @@ __device__ __forceinline__ void stream_nn8(const uint32_t* p, uint32_t (&i)[8])
 }
 
 // up to N (<= 7) consecutive entries: indices first, then their gathers together, then the moments in order
-template <int HINT, int N>
-__device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __restrict__ p, uint32_t cnt, uint32_t i0, const float4& o,
-                                          uint64_t pol_keep, Moments& m, bool& ok)
+template <int HINT, int N, typename Acc>
+__device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __restrict__ p, uint32_t j0, uint32_t cnt, uint32_t i0, const float4& o,
+                                          uint64_t pol_keep, Acc& acc, bool& ok)
 {
     uint32_t i[N];
     float4 q[N];
@@ -336,11 +336,12 @@ __device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __r
 #pragma unroll
     for (int u = 0; u < N; ++u) q[u] = gather_point<HINT>(a.xyz4 + i[u], pol_keep);
 #pragma unroll
-    for (int u = 0; u < N; ++u) if ((uint32_t)u < cnt) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
+    for (int u = 0; u < N; ++u) if ((uint32_t)u < cnt) acc(j0 + u, q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
 }
 
-template <int HINT>
-__device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint32_t len, Moments& m)
+// acc(j, dx, dy, dz) is called for j = 0 .. len-1 in order, offsets relative to the row's first neighbour
+template <int HINT, typename Acc>
+__device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint32_t len, Acc& acc)
 {
     const uint32_t* __restrict__ p = a.nn + b;
     const uint32_t n = a.n_xyz;
@@ -349,10 +350,11 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
     const uint64_t pol_keep = HINT >= 3 ? l2_policy_evict_last() : 0;
     const float4 o = gather_point<HINT>(a.xyz4 + i0, pol_keep);   // origin of the shifted moments; its own term is zero
     bool ok = true;
+    acc(0u, 0.f, 0.f, 0.f);
     uint32_t j = 1;
     // head: up to the next 32-byte boundary of the stream (whatever the alignment of nn itself)
     const uint32_t nh = min((uint32_t)((0u - (uint32_t)reinterpret_cast<uintptr_t>(p + 1)) & 31u) >> 2, len - 1u);
-    if (nh) { walk_some<HINT, 7>(a, p + j, nh, i0, o, pol_keep, m, ok); j += nh; }
+    if (nh) { walk_some<HINT, 7>(a, p + j, j, nh, i0, o, pol_keep, acc, ok); j += nh; }
     for (; j + 8 <= len; j += 8) {
         uint32_t i[8];
         stream_nn8<HINT>(p + j, i);
@@ -363,9 +365,9 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint3
             q[u] = gather_point<HINT>(a.xyz4 + i[u], pol_keep);
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) m.add(q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
+        for (int u = 0; u < 8; ++u) acc(j + u, q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
     }
-    if (j < len) walk_some<HINT, 7>(a, p + j, len - j, i0, o, pol_keep, m, ok);
+    if (j < len) walk_some<HINT, 7>(a, p + j, j, len - j, i0, o, pol_keep, acc, ok);
     return ok;
 }
 
@@ -396,7 +398,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
             if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
             else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
                 Moments m;
-                if (!walk_direct<HINT>(a, b, e - b, m)) atomicExch(a.err, 2);
+                auto acc = [&](uint32_t, float dx, float dy, float dz) { m.add(dx, dy, dz); };
+                if (!walk_direct<HINT>(a, b, e - b, acc)) atomicExch(a.err, 2);
                 else features11<float>(m.pca(e - b, a.eig_order), f);
             }
         }
@@ -404,6 +407,55 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
         for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
         store_rows<11>(a, t, s_out, s_rowid);
         __syncthreads();                                         // the staging buffers are re-used by the next tile
+    }
+}
+
+// compute_features_multiscale on the direct walker: 128 rows per CTA; every row's n_scales_pass x 11 block is
+// staged in shared memory (zeros where the row is too short, pgeof.hpp:193) and written as one contiguous run
+__global__ void __launch_bounds__(kRows, 8) multiscale_direct_kernel(const FeatArgs a)
+{
+    extern __shared__ __align__(16) float s_ms[];                   // [kRows][n_scales_pass * 11]
+    __shared__ uint32_t s_rowid[kRows];
+    const uint32_t r0 = blockIdx.x * kRows, rows = min((uint32_t)kRows, a.n_rows - r0);
+    const uint32_t W = a.n_scales_pass * 11;
+    float* mine = s_ms + threadIdx.x * W;
+    for (uint32_t i = 0; i < W; ++i) mine[i] = 0.f;
+    uint32_t row = r0 + threadIdx.x;
+    if (threadIdx.x < rows && a.order) row = __ldg(a.order + row);
+    s_rowid[threadIdx.x] = row;
+    if (threadIdx.x < rows) {
+        const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+        if (e < b || e > a.nnz) atomicExch(a.err, 1);
+        else {
+            const uint32_t len = e - b;
+            uint32_t n_fit = 0;                                     // scales of this pass the row is long enough for
+            while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
+            if (n_fit && a.scales[n_fit - 1] > 0) {
+                Moments m;
+                uint32_t s = 0;
+                while (s < n_fit && a.scales[s] == 0) ++s;           // k_s = 0 is rejected on the host; defensive
+                auto acc = [&](uint32_t j, float dx, float dy, float dz) {
+                    m.add(dx, dy, dz);
+                    while (s < n_fit && a.scales[s] == j + 1) {
+                        float f[11];
+                        features11<float>(m.pca(j + 1, a.eig_order), f);
+#pragma unroll
+                        for (int i = 0; i < 11; ++i) mine[s * 11 + i] = f[i];
+                        ++s;
+                    }
+                };
+                if (!walk_direct<0>(a, b, a.scales[n_fit - 1], acc)) {
+                    atomicExch(a.err, 2);
+                    for (uint32_t i = 0; i < W; ++i) mine[i] = 0.f;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const size_t stride = (size_t)a.n_scales_total * 11;
+    for (uint32_t i = threadIdx.x; i < rows * W; i += kRows) {
+        const uint32_t r = i / W, f = i - r * W;
+        a.out[(size_t)s_rowid[r] * stride + (size_t)a.scale_base * 11 + f] = s_ms[i];
     }
 }
 
@@ -779,7 +831,8 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
     DeviceBuffer err;
     PGEOF_TRY(err.alloc(sizeof(int), stream));
     PGEOF_CUDA(cudaMemsetAsync(err.ptr, 0, sizeof(int), stream));
-    PGEOF_CUDA(cudaMemsetAsync(out, 0, n_rows * n_scales * 11 * sizeof(float), stream));   // calloc semantics, pgeof.hpp:175
+    if (env_int("PGEOF_FEATURES_LAYOUT", 1) == 0)   // the direct kernel writes every element itself (zeros where a row is too short)
+        PGEOF_CUDA(cudaMemsetAsync(out, 0, n_rows * n_scales * 11 * sizeof(float), stream));   // calloc semantics, pgeof.hpp:175
     FeatArgs a;
     PGEOF_TRY(make_args(&a, xyz, n_xyz, nn, nnz, nn_ptr, n_rows, eig_order, out, err.as<int>(), 11));
     a.n_scales_total = (uint32_t)n_scales;
@@ -791,7 +844,8 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
         a.scale_base = (uint32_t)base;
         a.n_scales_pass = (uint32_t)std::min<size_t>(kMaxScalesPerPass, n_scales - base);
         for (uint32_t s = 0; s < a.n_scales_pass; ++s) a.scales[s] = k_scales_host[base + s];
-        PGEOF_TRY(launch_tiles(multiscale_kernel, "multiscale", a, fixed + (size_t)a.nn_cap * 4, stream));
+        if (env_int("PGEOF_FEATURES_LAYOUT", 1) == 0) PGEOF_TRY(launch_tiles(multiscale_kernel, "multiscale", a, fixed + (size_t)a.nn_cap * 4, stream));
+        else PGEOF_TRY(launch_tiles(multiscale_direct_kernel, "multiscale", a, (size_t)kRows * a.n_scales_pass * 11 * sizeof(float), stream));
     }
     return device_flag_check(err.as<int>(), stream, "compute_features_multiscale");
 }

@@ -275,7 +275,8 @@ struct TileCfg {
     static constexpr int STAGE_BYTES = CMAX * 16;
     static constexpr int BAR_BYTES = 16;
     static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
-    static constexpr int MAX_PASSES = 6;           // passes ((y, z) rows straddled, halved regions) before a warp falls back
+    static constexpr int MAX_PASSES = 12;          // passes ((y, z) rows straddled, halved regions, radius retries) before a warp falls back
+    static constexpr int RETRY_MIN = 5;            // lanes that must fail the same way before they are re-queued with another radius
     // a list entry / sort key is (bits(d2) & ~SLOT_MASK) | staged slot: 22 bits of distance order the
     // network, the slot finds the candidate again when the exact (d2, index) pair is rebuilt
     static constexpr uint32_t SLOT_BITS = 10;
@@ -341,11 +342,16 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
     unsigned remaining = __ballot_sync(kFull, valid);
     unsigned slow = 0;                       // lanes finished by the generic routine
     float rhint = 0.f;                       // ... which starts from this radius (0: from the local density)
+    // feedback for data the uniform-density seed misjudges (surfaces, lines, clusters): lanes whose ball held too few /
+    // too many points are re-queued ONCE OR TWICE as a group with a radius factor derived from the count they saw
+    float rmul = 1.f;                        // this lane's factor on the density-seeded radius
+    uint32_t retry = 0;                      // bits 0-1: re-queues so far, bits 2-3: class (0 first try, 1 grow, 2 shrink)
     for (int pass = 0; remaining; ++pass) {
         // ---- the lanes of this pass: queries in the (y, z) cell row of the first remaining lane ----
         const int leader = __ffs(remaining) - 1;
         const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
-        unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow);
+        const uint32_t lcls = __shfl_sync(kFull, retry >> 2, leader);
+        unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow && (retry >> 2) == lcls);
         remaining &= ~active;
         if (pass >= Cfg::MAX_PASSES) {
             slow |= active;
@@ -385,7 +391,9 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 c = __reduce_add_sync(kFull, c);
                 nc = __reduce_add_sync(kFull, nc);
                 const float rho = fmaxf((float)c, 1.f) / ((float)max(nc, 1) * g.hx * g.h * g.h);
-                R = cbrtf(a.target / (4.18879f * rho));
+                // positive floats order like their bit patterns
+                const float rm = __uint_as_float(__reduce_max_sync(kFull, mine ? __float_as_uint(rmul) : 0u));
+                R = cbrtf(a.target / (4.18879f * rho)) * rm;
             }
 
             // candidate region: cells meeting the dilated box; one contiguous span per (y, z) row
@@ -476,6 +484,25 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         bool ok = mine && cnt >= k && cnt <= (uint32_t)NLOAD;
         // radius the generic routine starts from if this lane leaves the fast path: scaled by the count seen here
         if (mine) rhint = R * (cnt < k ? fminf(cbrtf(1.25f * a.target / fmaxf((float)cnt, 2.f)), 3.f) : (cnt > (uint32_t)NLOAD ? 0.88f : 1.f));
+        // re-queue groups of lanes the seeded radius failed (>= RETRY_MIN of them: a pass costs as much as ~8 generic queries)
+        unsigned requeued = 0;
+        if (pass + 2 < Cfg::MAX_PASSES) {
+            const bool can = mine && (retry & 3u) < 2u;
+            const unsigned sh = __ballot_sync(kFull, can && cnt < k), ov = __ballot_sync(kFull, can && cnt > (uint32_t)NLOAD);
+            if (__popc(sh) >= Cfg::RETRY_MIN) {
+                if ((sh >> lane) & 1u) {
+                    // count ~ R^d with d between 2 (surface) and 3 (volume): exponent 1/2.5
+                    rmul *= fminf(fmaxf(exp2f(0.4f * log2f(1.3f * a.target / fmaxf((float)cnt, 1.f))), 1.15f), 3.f);
+                    retry = ((retry & 3u) + 1u) | (1u << 2);
+                }
+                requeued |= sh;
+            }
+            if (__popc(ov) >= Cfg::RETRY_MIN) {
+                if ((ov >> lane) & 1u) { rmul *= 0.7f; retry = ((retry & 3u) + 1u) | (2u << 2); }
+                requeued |= ov;
+            }
+            remaining |= requeued;
+        }
         if (a.stats) {
             const unsigned sh = __ballot_sync(kFull, mine && cnt < k), ov = __ballot_sync(kFull, mine && cnt > (uint32_t)NLOAD);
             const uint32_t sv = __reduce_add_sync(kFull, mine ? cnt : 0u);
@@ -564,7 +591,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 }
             }
         }
-        slow |= __ballot_sync(kFull, mine && !ok);
+        slow |= __ballot_sync(kFull, mine && !ok) & ~requeued;
         __syncwarp();
         // ---- write the finished rows, one coalesced row at a time ---------------------------------
         {
