@@ -67,6 +67,20 @@ __global__ void __launch_bounds__(kThreads) cell_count_kernel(GridView g, const 
     rank[i] = base + (uint32_t)__popc(peers & lanemask_lt());
 }
 
+// sum of c^2 over the cell counts: sum c^2 / n is the occupancy of the cell an average POINT lives in.  Uniform data:
+// mean occupancy + 1; a cloud of surfaces / clusters in a mostly empty bounding box: orders of magnitude more.
+__global__ void __launch_bounds__(kThreads) occupancy_kernel(const uint32_t* __restrict__ counts, size_t n_cells, unsigned long long* __restrict__ sum_sq)
+{
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long c = __ldg(counts + i);
+        acc += c * c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum_sq, acc);
+}
+
 __global__ void __launch_bounds__(kThreads) scatter_kernel(GridView g, const float* __restrict__ xyz, size_t n,
                                                            const uint32_t* __restrict__ cell_start,
                                                            const uint32_t* __restrict__ rank, float4* __restrict__ out)
@@ -216,47 +230,66 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
     }
     // 2. cell edge
     double h = cell_edge;
-    if (!(h > 0)) {
+    const bool adaptive = !(h > 0);
+    if (adaptive) {
         double vol = 1; int dims = 0;
         for (int d = 0; d < 3; ++d) if (ext[d] > 0) { vol *= ext[d]; ++dims; }
         h = dims ? std::pow(vol * std::max(1.0f, target_occupancy) / (double)n, 1.0 / dims) : 1.0;
     }
-    // float32 cannot resolve cells much finer than an ulp of the coordinates
-    h = std::max(h, std::max(maxabs * 1e-5, 1e-30));
     const size_t cap = max_cells_for(n);
-    int xf = std::max(1, std::min(x_refine, 16));
-    int nc[3];
-    for (;;) {
-        double cells = 1;
-        for (int d = 0; d < 3; ++d) {
-            const double edge = d == 0 ? h / xf : h;
-            const double c = std::floor(ext[d] / edge) + 1;
-            nc[d] = (int)std::min(c, 2e9);
-            cells *= c;
-        }
-        if (cells <= (double)cap) break;
-        if (xf > 1) xf >>= 1; else h *= 1.26;
-    }
     GridView& g = out->view;
-    for (int d = 0; d < 3; ++d) { g.lo[d] = lo[d]; g.n[d] = nc[d]; }
-    g.h = (float)h;
-    g.inv_h = 1.0f / g.h;
-    g.hx = (float)(h / xf);
-    g.inv_hx = 1.0f / g.hx;
-    g.xf = xf;
-    g.slack = (float)((2.0 * maxabs + h) * 9.5367431640625e-7);   // 2^-20
-    g.n_pts = (uint32_t)n;
-    out->n_cells = (size_t)nc[0] * nc[1] * nc[2];
-    // 3. histogram -> scan -> scatter
-    PGEOF_TRY(out->cell_start.alloc((out->n_cells + 1) * sizeof(uint32_t), stream));
-    PGEOF_TRY(out->pts.alloc(n * sizeof(float4), stream));
-    DeviceBuffer rank;
+    DeviceBuffer rank, stat;
     PGEOF_TRY(rank.alloc(n * sizeof(uint32_t), stream));
-    uint32_t* cs = out->cell_start.as<uint32_t>();
-    PGEOF_CUDA(cudaMemsetAsync(cs, 0, (out->n_cells + 1) * sizeof(uint32_t), stream));
     const unsigned blocks = (unsigned)((n + kThreads - 1) / kThreads);
-    cell_count_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>());
-    PGEOF_LAUNCH_CHECK();
+    uint32_t* cs = nullptr;
+    for (int attempt = 0;; ++attempt) {
+        // float32 cannot resolve cells much finer than an ulp of the coordinates
+        h = std::max(h, std::max(maxabs * 1e-5, 1e-30));
+        int xf = std::max(1, std::min(x_refine, 16));
+        int nc[3];
+        for (;;) {
+            double cells = 1;
+            for (int d = 0; d < 3; ++d) {
+                const double edge = d == 0 ? h / xf : h;
+                const double c = std::floor(ext[d] / edge) + 1;
+                nc[d] = (int)std::min(c, 2e9);
+                cells *= c;
+            }
+            if (cells <= (double)cap) break;
+            if (xf > 1) xf >>= 1; else h *= 1.26;
+        }
+        for (int d = 0; d < 3; ++d) { g.lo[d] = lo[d]; g.n[d] = nc[d]; }
+        g.h = (float)h;
+        g.inv_h = 1.0f / g.h;
+        g.hx = (float)(h / xf);
+        g.inv_hx = 1.0f / g.hx;
+        g.xf = xf;
+        g.slack = (float)((2.0 * maxabs + h) * 9.5367431640625e-7);   // 2^-20
+        g.n_pts = (uint32_t)n;
+        out->n_cells = (size_t)nc[0] * nc[1] * nc[2];
+        // 3. histogram
+        PGEOF_TRY(out->cell_start.alloc((out->n_cells + 1) * sizeof(uint32_t), stream));
+        cs = out->cell_start.as<uint32_t>();
+        PGEOF_CUDA(cudaMemsetAsync(cs, 0, (out->n_cells + 1) * sizeof(uint32_t), stream));
+        cell_count_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>());
+        PGEOF_LAUNCH_CHECK();
+        if (!adaptive || attempt >= 2) break;
+        // 3b. the edge above assumes the points fill their bounding box.  If the cell an average point lives in is far
+        // fuller than intended (surfaces / clusters in a mostly empty box), shrink the cells and count again.
+        if (!stat.ptr) PGEOF_TRY(stat.alloc(sizeof(unsigned long long), stream));
+        PGEOF_CUDA(cudaMemsetAsync(stat.ptr, 0, sizeof(unsigned long long), stream));
+        occupancy_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(cs, out->n_cells, stat.as<unsigned long long>());
+        PGEOF_LAUNCH_CHECK();
+        unsigned long long sum_sq = 0;
+        PGEOF_CUDA(cudaMemcpyAsync(&sum_sq, stat.ptr, sizeof(sum_sq), cudaMemcpyDeviceToHost, stream));
+        PGEOF_CUDA(cudaStreamSynchronize(stream));
+        const double seen = (double)sum_sq / (double)n;                                  // occupancy seen by a point (x-refined cells)
+        const double want = std::max(1.0f, target_occupancy) / xf + 1.0;                  // uniform data: mean + 1
+        if (seen <= 2.5 * want || out->n_cells * 2 > cap) break;
+        h *= std::max(0.25, std::pow(want / seen, 1.0 / 2.5));                            // between a surface (1/2) and a volume (1/3)
+    }
+    // 4. scan -> scatter
+    PGEOF_TRY(out->pts.alloc(n * sizeof(float4), stream));
     PGEOF_TRY(exclusive_scan_u32(cs, out->n_cells, stream));
     scatter_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), out->pts.as<float4>());
     PGEOF_LAUNCH_CHECK();

@@ -62,6 +62,7 @@ struct SearchArgs {
     float* sqr_dist;
     uint32_t* nn_ptr;        // RADIUS_COUNT: per-row counts out; RADIUS_CSR: row offsets in
     unsigned long long* stats;   // optional tile-kernel counters (PGEOF_KNN_STATS=1), else null
+    uint32_t flags;          // debugging switches (PGEOF_KNN_FLAGS): 1 = volume-only radius seed, 2 = no radius retries
     uint2* slow_list;        // tile kernel: (query position, bits(radius hint)) of the queries left to knn_slow_kernel
     uint32_t* slow_count;
 };
@@ -270,13 +271,14 @@ struct TileCfg {
     static constexpr int LCAP = NLOAD + 1 + SINK;  // list entries per lane
     static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
     static constexpr int WARPS = NWARPS;
-    static constexpr int CMAX = NLOAD <= 96 ? 896 : 832;   // candidates staged per pass (16 B each), multiple of 8
+    static constexpr int CMAX = NLOAD <= 96 ? 872 : 808;   // candidates staged per pass (16 B each), multiple of 8
     static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
     static constexpr int STAGE_BYTES = CMAX * 16;
-    static constexpr int BAR_BYTES = 16;
+    static constexpr int BAR_BYTES = 16 + 3 * 128;   // mbarrier + three per-lane words kept out of the register file (see below)
     static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
     static constexpr int MAX_PASSES = 12;          // passes ((y, z) rows straddled, halved regions, radius retries) before a warp falls back
-    static constexpr int RETRY_MIN = 5;            // lanes that must fail the same way before they are re-queued with another radius
+    static constexpr int RETRY_MIN = 16;           // lanes that must fail the same way before they are re-queued with another radius
+                                                   // (half a warp: uniform data never gets there, a surface or a cluster does at once)
     // a list entry / sort key is (bits(d2) & ~SLOT_MASK) | staged slot: 22 bits of distance order the
     // network, the slot finds the candidate again when the exact (d2, index) pair is rebuilt
     static constexpr uint32_t SLOT_BITS = 10;
@@ -341,17 +343,20 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 
     unsigned remaining = __ballot_sync(kFull, valid);
     unsigned slow = 0;                       // lanes finished by the generic routine
-    float rhint = 0.f;                       // ... which starts from this radius (0: from the local density)
+    // per-lane state that lives across passes sits in shared memory: the sorting network leaves no register to spare
+    float* const s_hint = reinterpret_cast<float*>(bar + 2) + lane;   // radius the generic routine starts from (0: local density)
     // feedback for data the uniform-density seed misjudges (surfaces, lines, clusters): lanes whose ball held too few /
     // too many points are re-queued ONCE OR TWICE as a group with a radius factor derived from the count they saw
-    float rmul = 1.f;                        // this lane's factor on the density-seeded radius
-    uint32_t retry = 0;                      // bits 0-1: re-queues so far, bits 2-3: class (0 first try, 1 grow, 2 shrink)
+    float* const s_rmul = s_hint + 32;       // this lane's factor on the density-seeded radius
+    uint32_t* const s_retry = reinterpret_cast<uint32_t*>(s_hint + 64);   // bits 0-1: re-queues so far, bits 2-3: class (0 first try, 1 grow, 2 shrink)
+    *s_hint = 0.f; *s_rmul = 1.f; *s_retry = 0u;
     for (int pass = 0; remaining; ++pass) {
         // ---- the lanes of this pass: queries in the (y, z) cell row of the first remaining lane ----
         const int leader = __ffs(remaining) - 1;
         const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
-        const uint32_t lcls = __shfl_sync(kFull, retry >> 2, leader);
-        unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow && (retry >> 2) == lcls);
+        const uint32_t cls = *s_retry >> 2;
+        const uint32_t lcls = __shfl_sync(kFull, cls, leader);
+        unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow && cls == lcls);
         remaining &= ~active;
         if (pass >= Cfg::MAX_PASSES) {
             slow |= active;
@@ -376,24 +381,38 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             const int cxb = __reduce_max_sync(kFull, mine ? cqx : -1);
             const int cy = __shfl_sync(kFull, cqy, leader), cz = __shfl_sync(kFull, cqz, leader);
 
-            // density of the block around them -> search radius R
+            // density and SHAPE of the block around them -> search radius R.  The 3 x 3 (y, z) rows of the block hold
+            // counts c_l; m = (sum c)^2 / sum c^2 is the number of rows the points effectively occupy: 9 for a filled
+            // volume, 3 for a surface, 1 for a line along x.  The ball is sized for a structure of dimension
+            // d = 1 + log3(m) whose density is that of the occupied rows (a uniform cloud gives d = 2.99; next to the
+            // domain boundary the empty outside rows lower d and enlarge the ball, as they should).
             {
                 const int bx0 = max(cxa - g.xf, 0), bx1 = min(cxb + g.xf, g.n[0] - 1);
-                int c = 0, nc = 0;
+                float c = 0.f;
                 if (lane < 9) {
                     const int by = cy + lane % 3 - 1, bz = cz + lane / 3 - 1;
                     if (by >= 0 && by < g.n[1] && bz >= 0 && bz < g.n[2]) {
                         const uint32_t rb = ((uint32_t)bz * (uint32_t)g.n[1] + (uint32_t)by) * (uint32_t)g.n[0];
-                        c = (int)(__ldg(g.cell_start + rb + bx1 + 1) - __ldg(g.cell_start + rb + bx0));
-                        nc = bx1 - bx0 + 1;
+                        c = (float)(__ldg(g.cell_start + rb + bx1 + 1) - __ldg(g.cell_start + rb + bx0));
                     }
                 }
-                c = __reduce_add_sync(kFull, c);
-                nc = __reduce_add_sync(kFull, nc);
-                const float rho = fmaxf((float)c, 1.f) / ((float)max(nc, 1) * g.hx * g.h * g.h);
+                float s1 = c, s2 = c * c;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) { s1 += __shfl_xor_sync(kFull, s1, o); s2 += __shfl_xor_sync(kFull, s2, o); }
+                s1 = fmaxf(__shfl_sync(kFull, s1, 0), 1.f);
+                s2 = fmaxf(__shfl_sync(kFull, s2, 0), 1.f);
+                const float m = fminf(fmaxf(s1 * s1 / s2, 1.f), 9.f);
+                const float d = 1.f + log2f(m) * 0.6309298f;                               // 1 / log2(3)
+                const float rho = s1 / (m * (float)(bx1 - bx0 + 1) * g.hx * g.h * g.h);     // density inside the occupied rows
+                const float T = a.target;
+                const float l3 = log2f(T / (4.18879f * rho)) * (1.f / 3.f);                 // volume:  4/3 pi R^3 rho = T
+                const float l2 = log2f(T / (3.14159265f * rho * g.h)) * 0.5f;               // surface: pi R^2 (rho h) = T
+                const float l1 = log2f(T / (2.f * rho * g.h * g.h));                        // line:    2 R (rho h^2) = T
+                float lr = d >= 2.f ? (d - 2.f) * l3 + (3.f - d) * l2 : (d - 1.f) * l2 + (2.f - d) * l1;
+                if (a.flags & 1u) lr = log2f(T / (4.18879f * s1 / (9.f * (float)(bx1 - bx0 + 1) * g.hx * g.h * g.h))) * (1.f / 3.f);
                 // positive floats order like their bit patterns
-                const float rm = __uint_as_float(__reduce_max_sync(kFull, mine ? __float_as_uint(rmul) : 0u));
-                R = cbrtf(a.target / (4.18879f * rho)) * rm;
+                const float rm = __uint_as_float(__reduce_max_sync(kFull, mine ? __float_as_uint(*s_rmul) : 0u));
+                R = exp2f(lr) * rm;
             }
 
             // candidate region: cells meeting the dilated box; one contiguous span per (y, z) row
@@ -483,22 +502,23 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         const uint32_t cnt = (waddr - waddr0) / (S * 4);
         bool ok = mine && cnt >= k && cnt <= (uint32_t)NLOAD;
         // radius the generic routine starts from if this lane leaves the fast path: scaled by the count seen here
-        if (mine) rhint = R * (cnt < k ? fminf(cbrtf(1.25f * a.target / fmaxf((float)cnt, 2.f)), 3.f) : (cnt > (uint32_t)NLOAD ? 0.88f : 1.f));
+        if (mine) *s_hint = R * (cnt < k ? fminf(cbrtf(1.25f * a.target / fmaxf((float)cnt, 2.f)), 3.f) : (cnt > (uint32_t)NLOAD ? 0.88f : 1.f));
         // re-queue groups of lanes the seeded radius failed (>= RETRY_MIN of them: a pass costs as much as ~8 generic queries)
         unsigned requeued = 0;
-        if (pass + 2 < Cfg::MAX_PASSES) {
+        if (pass + 2 < Cfg::MAX_PASSES && !(a.flags & 2u)) {
+            const uint32_t retry = *s_retry;
             const bool can = mine && (retry & 3u) < 2u;
             const unsigned sh = __ballot_sync(kFull, can && cnt < k), ov = __ballot_sync(kFull, can && cnt > (uint32_t)NLOAD);
             if (__popc(sh) >= Cfg::RETRY_MIN) {
                 if ((sh >> lane) & 1u) {
                     // count ~ R^d with d between 2 (surface) and 3 (volume): exponent 1/2.5
-                    rmul *= fminf(fmaxf(exp2f(0.4f * log2f(1.3f * a.target / fmaxf((float)cnt, 1.f))), 1.15f), 3.f);
-                    retry = ((retry & 3u) + 1u) | (1u << 2);
+                    *s_rmul *= fminf(fmaxf(exp2f(0.4f * log2f(1.3f * a.target / fmaxf((float)cnt, 1.f))), 1.15f), 3.f);
+                    *s_retry = ((retry & 3u) + 1u) | (1u << 2);
                 }
                 requeued |= sh;
             }
             if (__popc(ov) >= Cfg::RETRY_MIN) {
-                if ((ov >> lane) & 1u) { rmul *= 0.7f; retry = ((retry & 3u) + 1u) | (2u << 2); }
+                if ((ov >> lane) & 1u) { *s_rmul *= 0.7f; *s_retry = ((retry & 3u) + 1u) | (2u << 2); }
                 requeued |= ov;
             }
             remaining |= requeued;
@@ -626,7 +646,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         uint32_t at = 0;
         if (lane == 0) at = atomicAdd(a.slow_count, (uint32_t)__popc(slow));
         at = __shfl_sync(kFull, at, 0);
-        if ((slow >> lane) & 1u) a.slow_list[at + __popc(slow & lanemask_lt())] = make_uint2(base + lane, __float_as_uint(rhint));
+        if ((slow >> lane) & 1u) a.slow_list[at + __popc(slow & lanemask_lt())] = make_uint2(base + lane, __float_as_uint(*s_hint));
     }
 }
 
@@ -733,7 +753,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     const float4* qrec;
     if (query == data && n_query == n_data) qrec = grid.view.pts;   // self query: reuse the sorted cloud
     else { PGEOF_TRY(grid_sort_queries(grid, query, n_query, stream, &qsorted)); qrec = qsorted.as<float4>(); }
-    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr, nullptr, nullptr};
+    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr, (uint32_t)env_float("PGEOF_KNN_FLAGS", 0.f), nullptr, nullptr};
     if (tile) {
         DeviceBuffer stats, slow;
         PGEOF_TRY(slow.alloc(16 + n_query * sizeof(uint2), stream));
@@ -754,10 +774,13 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
             unsigned long long h[ST_N];
             PGEOF_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
             PGEOF_CUDA(cudaStreamSynchronize(stream));
-            std::fprintf(stderr, "[pgeof knn tile] n=%zu k=%u target=%.1f: slow short=%llu over=%llu tie=%llu region=%llu | fixed rows=%llu "
-                         "passes=%llu candidates/pass=%.1f survivors/query=%.1f\n", n_query, k, target, h[ST_SHORT], h[ST_OVER], h[ST_TIE],
-                         h[ST_REGION], h[ST_FIXED], h[ST_PASSES], (double)h[ST_CANDS] / (double)std::max(h[ST_PASSES], 1ull),
-                         (double)h[ST_SURV] / (double)n_query);
+            uint32_t n_slow = 0;
+            PGEOF_CUDA(cudaMemcpyAsync(&n_slow, a.slow_count, sizeof(n_slow), cudaMemcpyDeviceToHost, stream));
+            PGEOF_CUDA(cudaStreamSynchronize(stream));
+            std::fprintf(stderr, "[pgeof knn tile] n=%zu k=%u target=%.1f h=%.3f: generic queries=%u | per-pass events: short=%llu over=%llu tie=%llu region=%llu "
+                         "fixed rows=%llu passes=%llu candidates/pass=%.1f survivors/query=%.1f\n", n_query, k, target, grid.view.h, n_slow,
+                         h[ST_SHORT], h[ST_OVER], h[ST_TIE], h[ST_REGION], h[ST_FIXED], h[ST_PASSES],
+                         (double)h[ST_CANDS] / (double)std::max(h[ST_PASSES], 1ull), (double)h[ST_SURV] / (double)n_query);
         }
         return st;
     }
