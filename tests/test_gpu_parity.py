@@ -396,6 +396,57 @@ def test_c_abi_called_directly_through_ctypes():
 
 
 # --------------------------------------------------------------------------------------------
+# paths added with the tile kernels: radius retries / adaptive grid, unaligned nn streams, slab shards
+# --------------------------------------------------------------------------------------------
+def test_knn_mixed_density_surfaces_clusters_bitexact():
+    """A dense sheet, a sparse volume, tight clusters and a line in one mostly empty box: the uniform-density radius
+    seed fails in every way here (group retries, region halving, adaptive cell edge, generic fallback)."""
+    rng = np.random.default_rng(11)
+    sheet = np.c_[rng.uniform(0, 60, (400000, 2)), rng.normal(0, 0.01, 400000)]
+    volume = rng.uniform(0, 60, (60000, 3)) * [1, 1, 0.5]
+    centers = rng.uniform(5, 55, (300, 3)) * [1, 1, 0.4]
+    clusters = (centers[rng.integers(0, 300, 150000)] + rng.normal(0, 0.15, (150000, 3)))
+    line = np.c_[rng.uniform(0, 60, 20000), np.full(20000, 30.0), np.full(20000, 12.0)] + rng.normal(0, 0.002, (20000, 3))
+    xyz = np.concatenate([sheet, volume, clusters, line]).astype(np.float32)[rng.permutation(630000)]
+    rows = rng.choice(len(xyz), 12000, replace=False)
+    for k in (20, 50):
+        idx, d2 = pgeof.knn_search(xyz, xyz, k)
+        _assert_search_equal((idx[rows], d2[rows]), cpu.knn_search(xyz, xyz[rows], k))
+        assert (np.diff(d2, axis=1) >= 0).all() and (idx[:, 0] == np.arange(len(xyz))).sum() > 0.99 * len(xyz)
+
+
+def test_features_unaligned_nn_stream_on_device():
+    """nn as a view that starts 4 bytes into an allocation (the 256-bit stream loads need their own alignment head)."""
+    import torch
+    xyz = synth.uniform_cloud(40000, seed=21)
+    idx, _ = cpu.knn_search(xyz, xyz, 23)                                      # odd row length: every alignment occurs
+    nn, nn_ptr = knn_csr(idx)
+    ref = pgeof.compute_features(xyz, nn, nn_ptr)
+    t = torch.from_numpy(xyz).cuda()
+    for shift in (1, 2, 3, 5):
+        big = torch.zeros(len(nn) + shift, dtype=torch.int32, device="cuda")
+        big[shift:] = torch.from_numpy(nn.view(np.int32)).cuda()
+        got = pgeof.compute_features(t, big[shift:].view(torch.uint32), torch.from_numpy(nn_ptr.view(np.int32)).cuda().view(torch.uint32))
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)
+        ms = pgeof.compute_features_multiscale(t, big[shift:].view(torch.uint32), torch.from_numpy(nn_ptr.view(np.int32)).cuda().view(torch.uint32), [5, 23])
+        np.testing.assert_array_equal(ms.cpu().numpy()[:, 1], ref)
+
+
+def test_slab_shards_reproduce_the_single_device_rows():
+    import torch
+    from point_geometric_features_b200 import shard
+    xyz = synth.uniform_cloud(200000, seed=31)
+    t = torch.from_numpy(xyz).cuda()
+    full_idx, full_d2 = pgeof.knn_search(t, t, 50)
+    seen = torch.zeros(len(xyz), dtype=torch.bool, device="cuda")
+    for r in range(4):
+        rows, idx, d2, feats = shard.knn_features_shard(t, 50, r, 4)
+        assert bool((idx.view(torch.int32) == full_idx.view(torch.int32)[rows]).all()) and bool((d2 == full_d2[rows]).all())
+        seen[rows] = True
+    assert bool(seen.all())
+
+
+# --------------------------------------------------------------------------------------------
 # BASELINE full size (10M points, k = 50): size-independent properties + sampled oracle rows
 # --------------------------------------------------------------------------------------------
 def test_metric_workload_full_size_properties():
