@@ -147,7 +147,7 @@ def cpu_step(cpu, xyz, k):
     return cpu.compute_features(xyz, nn, nn_ptr, 1, "literal", f64=False)
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, real_stdout):
     """--impl reference: the reference's CPU path.  The reference binary cannot be built here (empty
     third_party submodules), so this times oracle/cpu_ref.cpp, the C++ restatement (kind "port")."""
     if rank != 0:
@@ -170,16 +170,32 @@ def run_reference(args, rank):
                                             "points": args.points, "knn": args.knn, "sample_points": n_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.hardware_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(real_stdout, line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: NCCL / torchrun banners written to fd 1 by native code go to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(real_stdout)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+
+def emit(real_stdout, line):
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
+
+def _main(real_stdout):
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
 
     # The drop-in API returns freshly allocated outputs (2 x 2 GB + 0.44 GB per step here), served by torch's caching
@@ -348,14 +364,14 @@ def main():
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "uniform [0,200)^3 float32 cloud (seed 0), knn_search(k=%d) -> CSR view -> compute_features (11 features); grid build included in every step" % k,
                            "points": n_total, "knn": k, "rows_per_rank": rows_dev,
-                           "parallelism": "query-sharded x%d (z slabs of ~n/N points from histogram quantiles, computed inside the step), cloud and grid replicated, no data-path collective; e2e shards by contiguous row range" % world,
+                           "parallelism": "query-sharded x%d (z slabs of ~n/N points from sample quantiles, computed inside the step), cloud and grid replicated, no data-path collective; e2e shards by contiguous row range" % world,
                            "l2": "512 MiB buffer zeroed between timed iterations; per-step working set %.1f GB >> 126 MB L2" % ((rows * (k * 12 + 44) + n * 28) / 1e9),
                            "eig_order": "literal"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": int(own_launches), "gpu_launches_per_step": own_launches / args.steps,
                 "wall_s_timed_region": t_wall1 - t_wall0,
                 "step_ms_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)]}
-        print(json.dumps(line), flush=True)
+        emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
 

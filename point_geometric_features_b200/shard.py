@@ -11,8 +11,8 @@ Which rows a rank owns is a free choice.  ``shard_range`` (contiguous row ranges
 cloud in random order, leaves every rank with queries spread thinly over the WHOLE volume: the kNN tile
 kernel shares one candidate region between 32 neighbouring queries, so its cost per query grows as the
 queries thin out (measured: 5 M of 10 M random rows cost 7.1 ms against 7.7 ms for all 10 M).
-``spatial_shard`` therefore gives rank r a SLAB along one axis holding ~n/world points (histogram
-quantiles, computed identically on every rank from the replicated cloud, no collective), which keeps the
+``spatial_shard`` therefore gives rank r a SLAB along one axis holding ~n/world points (quantiles of a
+sorted sample, computed identically on every rank from the replicated cloud, no collective), which keeps the
 query density of a single-GPU run; ``gather_rows_indexed`` puts such row blocks back in input order.
 
 ``gather_rows`` / ``gather_rows_indexed`` (optional, off the timed path) reassemble per-rank row blocks
@@ -41,10 +41,11 @@ def local_knn_csr(n_local, k, torch, device):
     return (torch.arange(n_local + 1, device=device, dtype=torch.int64) * k).to(torch.uint32)
 
 
-def spatial_shard(xyz, rank, world, axis=2, bins=4096):
-    """Row ids (ascending, int64) of rank ``rank``'s slab along ``axis``: the slabs partition the rows and hold
-    n/world points each up to the resolution of a ``bins``-bin histogram.  ``xyz`` is the replicated (n, 3)
-    cloud as a torch tensor (any device); every rank derives the same slab edges, so no exchange is needed."""
+def spatial_shard(xyz, rank, world, axis=2, sample=65536):
+    """Row ids (ascending, int64) of rank ``rank``'s slab along ``axis``.  The slabs partition the rows; their edges
+    are the k/world quantiles of a strided sample of ``sample`` coordinates (sorted on the device: a handful of small
+    kernels), so every slab holds n/world points up to the sampling error (~1 % at world = 8).  ``xyz`` is the
+    replicated (n, 3) cloud as a torch tensor (any device); every rank derives the same edges, so no exchange is needed."""
     import torch
 
     if world < 1 or not (0 <= rank < world):
@@ -53,15 +54,12 @@ def spatial_shard(xyz, rank, world, axis=2, bins=4096):
     if world == 1 or n == 0:
         return torch.arange(n, device=xyz.device)
     c = xyz[:, axis]
-    lo, hi = torch.aminmax(c)
-    scale = bins / torch.clamp(hi - lo, min=1e-30)
-    b = ((c - lo) * scale).to(torch.int64).clamp_(0, bins - 1)
-    cum = torch.cumsum(torch.bincount(b, minlength=bins), 0)
-    # slab r = bins [e_r, e_{r+1}): e_r = first bin whose cumulative count exceeds r * n / world
-    targets = torch.tensor([(r * n) // world for r in range(1, world)], device=xyz.device, dtype=cum.dtype)
-    inner = torch.searchsorted(cum, targets, right=True)
-    edges = torch.cat([inner.new_zeros(1), inner, inner.new_full((1,), bins)])
-    return torch.nonzero((b >= edges[rank]) & (b < edges[rank + 1])).squeeze(1)
+    s = torch.sort(c[:: max(1, n // sample)]).values
+    m = s.shape[0]
+    lo_ok = c >= s[(rank * m) // world] if rank > 0 else None
+    hi_ok = c < s[((rank + 1) * m) // world] if rank + 1 < world else None
+    mask = lo_ok if hi_ok is None else (hi_ok if lo_ok is None else lo_ok & hi_ok)
+    return torch.nonzero(mask).squeeze(1)
 
 
 def knn_features_shard(xyz, k, rank, world, k_min=1, spatial=True):
