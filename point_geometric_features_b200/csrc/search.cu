@@ -170,17 +170,10 @@ __device__ __forceinline__ void write_knn_row(const SearchArgs& a, uint32_t row,
 // one warp per query: kNN with k > 64 and the radius modes
 // ---------------------------------------------------------------------------------------
 template <int NSORT, int MODE>
-__global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, const SearchArgs a)
+__device__ __forceinline__ void search_one(const GridView& g, const SearchArgs& a, const float4 q4, u64* keybuf, int lane)
 {
     using Cfg = SearchCfg<NSORT, MODE>;
     constexpr int M = Cfg::M, CAP = Cfg::CAP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64* keybuf = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * CAP;
-    const uint32_t w = blockIdx.x * kWarps + warp;
-    if (w >= a.n_query) return;
-
-    const float4 q4 = __ldg(a.queries + w);
     const float qx = q4.x, qy = q4.y, qz = q4.z;
     const uint32_t row = __float_as_uint(q4.w);
     const uint32_t k = a.k;
@@ -260,6 +253,31 @@ __global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, c
     }
 }
 
+template <int NSORT, int MODE>
+__global__ void __launch_bounds__(kWarps * 32) search_kernel(const GridView g, const SearchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* keybuf = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * SearchCfg<NSORT, MODE>::CAP;
+    const uint32_t w = blockIdx.x * kWarps + warp;
+    if (w >= a.n_query) return;
+    search_one<NSORT, MODE>(g, a, __ldg(a.queries + w), keybuf, lane);
+}
+
+// the same routine over the queries a tile kernel queued (radius mode)
+template <int NSORT, int MODE>
+__global__ void __launch_bounds__(kWarps * 32) search_list_kernel(const GridView g, const SearchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64* keybuf = reinterpret_cast<u64*>(smem_raw) + (size_t)warp * SearchCfg<NSORT, MODE>::CAP;
+    const uint32_t n = *a.slow_count;
+    for (uint32_t w = blockIdx.x * kWarps + warp; w < n; w += gridDim.x * kWarps) {
+        search_one<NSORT, MODE>(g, a, __ldg(a.queries + a.slow_list[w].x), keybuf, lane);
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // one thread per query, one warp per 32 cell-sorted queries: kNN with k <= 64
 // ---------------------------------------------------------------------------------------
@@ -314,9 +332,10 @@ __device__ __forceinline__ uint32_t select_sort_network(uint32_t (&v)[NOUT + NEX
     return dropped;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS>
+template <int NOUT, int NEXTRA, int NWARPS, int MODE>
 __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
 {
+    static_assert(MODE == SEARCH_KNN || MODE == SEARCH_RADIUS, "tile kernel: kNN or padded radius search");
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     constexpr int M = NOUT / 32, NLOAD = Cfg::NLOAD, S = Cfg::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_tile[];
@@ -381,6 +400,11 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             const int cxb = __reduce_max_sync(kFull, mine ? cqx : -1);
             const int cy = __shfl_sync(kFull, cqy, leader), cz = __shfl_sync(kFull, cqz, leader);
 
+            if (MODE == SEARCH_RADIUS) {
+                // radius search: the ball is given (nn_search.hpp:98: r^2 = fl(r * r) decides, strictly)
+                const float r2 = __fmul_rn(a.radius, a.radius);
+                R = __fmul_ru(__fsqrt_ru(r2), 1.0001f);
+            } else
             // density and SHAPE of the block around them -> search radius R.  The 3 x 3 (y, z) rows of the block hold
             // counts c_l; m = (sum c)^2 / sum c^2 is the number of rows the points effectively occupy: 9 for a filled
             // volume, 3 for a surface, 1 for a line along x.  The ball is sized for a structure of dimension
@@ -473,7 +497,9 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 
         // ---- scan: every candidate is read once per warp (broadcast) and tested by all lanes ------
         // accept iff d2 <= t2 with t2 strictly inside R^2, so every accepted point is in the region
-        const float t2 = mine ? __fmul_rd(__fmul_rd(R, R), 0.9999f) : -1.f;
+        // radius mode: everything whose DEFINED distance is < r^2 must pass the fused filter -> r^2 (1 + 2^-18), rounded up
+        const float r2 = __fmul_rn(a.radius, a.radius);
+        const float t2 = !mine ? -1.f : (MODE == SEARCH_RADIUS ? (r2 > 0.f ? __fmul_ru(r2, 1.0000038147f) : -1.f) : __fmul_rd(__fmul_rd(R, R), 0.9999f));
         const float t2_safe = __fmul_rd(t2, 0.99999618530273f);   // t2 (1 - 2^-18)
         uint32_t* const wbase = list + lane;
         // shared-memory byte address of the lane's next free entry: advances by one stride per survivor;
@@ -500,12 +526,12 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 #undef PGEOF_TILE_APPEND
         __syncwarp();
         const uint32_t cnt = (waddr - waddr0) / (S * 4);
-        bool ok = mine && cnt >= k && cnt <= (uint32_t)NLOAD;
+        bool ok = mine && (MODE == SEARCH_RADIUS || cnt >= k) && cnt <= (uint32_t)NLOAD;
         // radius the generic routine starts from if this lane leaves the fast path: scaled by the count seen here
         if (mine) *s_hint = R * (cnt < k ? fminf(cbrtf(1.25f * a.target / fmaxf((float)cnt, 2.f)), 3.f) : (cnt > (uint32_t)NLOAD ? 0.88f : 1.f));
         // re-queue groups of lanes the seeded radius failed (>= RETRY_MIN of them: a pass costs as much as ~8 generic queries)
         unsigned requeued = 0;
-        if (pass + 2 < Cfg::MAX_PASSES && !(a.flags & 2u)) {
+        if (MODE == SEARCH_KNN && pass + 2 < Cfg::MAX_PASSES && !(a.flags & 2u)) {
             const uint32_t retry = *s_retry;
             const bool can = mine && (retry & 3u) < 2u;
             const unsigned sh = __ballot_sync(kFull, can && cnt < k), ov = __ballot_sync(kFull, can && cnt > (uint32_t)NLOAD);
@@ -536,8 +562,10 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         }
 
         // ---- sort: one thread per row, 32-bit keys in registers ---------------------------------
+        uint32_t need = k;                     // entries of the row that hold neighbours (radius mode: the rest is padding)
         uint32_t dropped;
         uint32_t bad[M] = {};                  // bit i: sorted entry i precedes entry i - 1 in the exact order
+        uint32_t nvalid = 0;                   // radius mode: kept entries whose defined distance is < r^2
         {
             uint32_t v[NLOAD];
 #pragma unroll
@@ -559,6 +587,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 const uint32_t id = __float_as_uint(p.w);
                 if (i > 0) bad[i / 32] |= ((uint32_t)i < cnt && (d < pd || (d == pd && id < pi))) ? (1u << (i % 32)) : 0u;
                 pd = d; pi = id;
+                if (MODE == SEARCH_RADIUS) nvalid += ((uint32_t)i < cnt && d < __float_as_uint(r2)) ? 1u : 0u;
                 plane_d[i * S] = d;
                 v[i] = id;
             }
@@ -599,9 +628,18 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             // the defined one: at most one truncation bucket (2^-13) off.  The row is exact iff
             //  (a) no dropped key can precede the k-th neighbour: bucket(dropped) >= bucket(k-th) + 2, and
             //  (b) no rejected candidate can: d2(k-th) <= t2 (1 - 2^-18) < defined d2 of anything rejected.
-            const uint32_t kth = plane_d[(k - 1) * S];
-            const bool tie = ok && ((dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u) ||
-                                    !(__uint_as_float(kth) <= t2_safe));
+            bool tie;
+            if (MODE == SEARCH_RADIUS) {
+                // rows: the min(nvalid, k) nearest.  Keys were only dropped if more than NOUT passed the filter; then the
+                // row must be full (k valid entries) and the dropped keys two buckets above its last entry, as in (a)
+                need = min(nvalid, k);
+                const uint32_t kth = plane_d[(max(need, 1u) - 1) * S];
+                tie = ok && dropped != 0xffffffffu && (need < k || (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u);
+            } else {
+                const uint32_t kth = plane_d[(k - 1) * S];
+                tie = ok && ((dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u) ||
+                             !(__uint_as_float(kth) <= t2_safe));
+            }
             if (tie) ok = false;
             if (a.stats) {
                 const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && any_bad);
@@ -622,13 +660,15 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 #pragma unroll 8
             for (int q = 0; q < 32; ++q) {
                 const uint32_t rowq = __shfl_sync(kFull, row, q);
+                const uint32_t needq = MODE == SEARCH_RADIUS ? __shfl_sync(kFull, need, q) : k;
                 const size_t o = (size_t)rowq * k + lane;
                 uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + o;
                 float* d2 = a.sqr_dist + o;
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const uint32_t e = r * 32 + lane;
-                    const uint32_t vi = plane_i[e * S + q], vd = plane_d[e * S + q];
+                    uint32_t vi = plane_i[e * S + q], vd = plane_d[e * S + q];
+                    if (MODE == SEARCH_RADIUS && e >= needq) { vi = 0xffffffffu; vd = 0u; }   // pad: -1 / 0 (nn_search.hpp:104,108)
                     const uint32_t on = (((okm >> q) & 1u) && e < k) ? 1u : 0u;
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
                                  "@p st.global.u32 [%0], %2;\n\t@p st.global.u32 [%1], %3;\n\t}"
@@ -687,18 +727,19 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS = 2>
+template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN>
 int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
-    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS>;
+    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE>;
     PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
     {
-        KernelTimer timer("knn_search", stream);
+        KernelTimer timer(MODE == SEARCH_KNN ? "knn_search" : "radius_search", stream);
         kern<<<blocks, Cfg::WARPS * 32, smem, stream>>>(g, a);
-        knn_slow_kernel<NOUT><<<148 * 4, kWarps * 32, 0, stream>>>(g, a);
+        if (MODE == SEARCH_KNN) knn_slow_kernel<NOUT><<<148 * 4, kWarps * 32, 0, stream>>>(g, a);
+        else search_list_kernel<NOUT, SEARCH_RADIUS><<<148 * 4, kWarps * 32, (size_t)kWarps * SearchCfg<NOUT, SEARCH_RADIUS>::CAP * sizeof(u64), stream>>>(g, a);
     }
     PGEOF_LAUNCH_CHECK();
     PGEOF_LAUNCH_CHECK();
@@ -735,7 +776,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     if (n_query > 0xfffffff0ull) { set_error("n_query too large"); return PGEOF_EINVAL; }
     Grid grid;
     float target = 0.f;
-    const bool tile = mode == SEARCH_KNN && k <= 64 && env_float("PGEOF_KNN_TILE", 1.f) != 0.f;
+    const bool tile = (mode == SEARCH_KNN ? env_float("PGEOF_KNN_TILE", 1.f) != 0.f : mode == SEARCH_RADIUS && env_float("PGEOF_RADIUS_TILE", 1.f) != 0.f) && k <= 64;
     if (mode == SEARCH_KNN) {
         // ball seeded to hold k + z sigma + 2 points.  Tile path: z balances the two ways a query leaves the
         // fast path (fewer than k survivors / more than the sorting network absorbs); cell edge h slightly
@@ -746,8 +787,9 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         PGEOF_TRY(grid_build(data, n_data, 0.f, occ, tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1, stream, &grid));
     } else {
         if (!(radius >= 0.f) || !std::isfinite(radius)) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
-        const float edge = radius * env_float("PGEOF_RADIUS_CELL_SCALE", 1.0f);
-        PGEOF_TRY(grid_build(data, n_data, edge > 0.f ? edge : 1.f, 0.f, 1, stream, &grid));
+        // tile path: cell edge just above the radius, so that the ball of a query reaches one cell row to either side
+        const float edge = radius * env_float("PGEOF_RADIUS_CELL_SCALE", tile ? 1.002f : 1.0f);
+        PGEOF_TRY(grid_build(data, n_data, edge > 0.f ? edge : 1.f, 0.f, tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1, stream, &grid));
     }
     DeviceBuffer qsorted;
     const float4* qrec;
@@ -767,7 +809,8 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
             a.stats = stats.as<unsigned long long>();
         }
         int st;
-        if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
+        if (mode == SEARCH_RADIUS) st = k <= 32 ? launch_tile<32, 32, 2, SEARCH_RADIUS>(grid.view, a, stream) : launch_tile<64, 32, 4, SEARCH_RADIUS>(grid.view, a, stream);
+        else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
         else if (k <= 52) st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
         else st = launch_tile<64, 64>(grid.view, a, stream);
         if (st == PGEOF_OK && want_stats) {
