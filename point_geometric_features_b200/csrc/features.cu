@@ -700,6 +700,7 @@ int env_int(const char* name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
+
 int prepare(FeatArgs* a, Prepass* p, cudaStream_t stream)
 {
     // 1. float4 re-pack of the cloud: one 128-bit load per gathered neighbour
@@ -792,7 +793,7 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
             a.out = tmp.as<float>();
             a.tma_out = 1;
         }
-        const int hint = env_int("PGEOF_FEATURES_HINT", 0);
+        const int hint = env_int("PGEOF_FEATURES_HINT", 0);   // 3: L2 evict_last gathers (no gain, with or without a persisting set-aside)
         const int cta = env_int("PGEOF_FEATURES_CTA", 512);
         int dev = 0, sms = 148;
         PGEOF_CUDA(cudaGetDevice(&dev));
@@ -808,7 +809,7 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
             return PGEOF_OK;
         };
         a.tma_out = a.tma_out && ((cta * 11 * 4) % 16 == 0);
-        if (hint == 4 && cta == 512) PGEOF_TRY(launch(features_direct_kernel<4, 512>, 512));
+        if (hint == 3 && cta == 512) PGEOF_TRY(launch(features_direct_kernel<3, 512>, 512));
         else if (cta == 128) PGEOF_TRY(launch(features_direct_kernel<0, 128>, 128));
         else if (cta == 256) PGEOF_TRY(launch(features_direct_kernel<0, 256>, 256));
         else if (cta == 1024) PGEOF_TRY(launch(features_direct_kernel<0, 1024>, 1024));
