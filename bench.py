@@ -297,9 +297,12 @@ def _main(real_stdout):
     alg = {"knn_search": (24 + 8 * k) * rows, "features": (48 + 16 * k) * rows}
     dom = max(("knn_search", "features"), key=lambda nme: kernels[nme]["ms_per_launch"])
     ach = alg[dom] / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+    # dram__bytes_read + dram__bytes_write per row from the latest `ncu --set full` capture (profiles/r1c_summary.md)
+    traffic_per_row = {"knn_search": 571.5, "features": 680.4}
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic_per_row[dom] * rows, "traffic_source": "profiles/r1c_summary.md (ncu --set full, 10 M rows, scaled by rows)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                "note": "search_kernel is issue-bound (distance + select + warp sort), not HBM-bound; see DESIGN.md",
+                "note": "knn tile kernel is FP32/ALU-issue bound (622 candidate evaluations + a 985-comparator sorting network per query), not HBM bound; the gather-bound feature kernel is the one to read against the HBM roofline (all_kernels.features); see DESIGN.md",
                 "all_kernels": {nme: {"ms": kernels[nme]["ms_per_launch"],
                                       "achieved_gbs": (alg[nme] / (kernels[nme]["ms_per_launch"] * 1e-3) / 1e9) if nme in alg and kernels[nme]["ms_per_launch"] > 0 else None}
                                 for nme in kernels}}
@@ -326,8 +329,11 @@ def _main(real_stdout):
             host_step()
         barrier()
         t0 = time.perf_counter()
+        e2e_ms = []
         for _ in range(e2e_steps):
+            ts = time.perf_counter()
             host_step()
+            e2e_ms.append(1e3 * (time.perf_counter() - ts))
         barrier()
         dt = time.perf_counter() - t0
         tm = torch.tensor([dt], device=dev, dtype=torch.float64)
@@ -338,6 +344,7 @@ def _main(real_stdout):
         d2h = rows * k * 8 + rows * 44
         e2e = {"value": n_total * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
+               "step_ms_min_median_max": [min(e2e_ms), statistics.median(e2e_ms), max(e2e_ms)],
                "path": "pgeof.knn_search(numpy) -> reshape/arange glue -> pgeof.compute_features(numpy); pinned host input, pinned pooled outputs"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
