@@ -289,7 +289,7 @@ struct TileCfg {
     static constexpr int LCAP = NLOAD + 1 + SINK;  // list entries per lane
     static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
     static constexpr int WARPS = NWARPS;
-    static constexpr int CMAX = NLOAD <= 96 ? 872 : 808;   // candidates staged per pass (16 B each), multiple of 8
+    static constexpr int CMAX = NLOAD <= 96 ? 872 : 1016;  // candidates staged per pass (16 B each), multiple of 8 (k > 52: balls of ~90 points need ~800)
     static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
     static constexpr int STAGE_BYTES = CMAX * 16;
     static constexpr int BAR_BYTES = 16 + 3 * 128;   // mbarrier + three per-lane words kept out of the register file (see below)
@@ -747,7 +747,11 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 }
 
 // survivors the tile kernel's sorting network absorbs for a given k
-inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= 52 ? 96 : 128); }
+float env_float(const char* name, float dflt);
+
+// largest k served by the 96-key network; above it (up to 64) the 128-key one
+inline uint32_t tile_wide_k() { return (uint32_t)env_float("PGEOF_KNN_WIDE_K", 64.f); }
+inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= tile_wide_k() ? 96 : 128); }
 
 template <int MODE>
 int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, cudaStream_t stream)
@@ -811,7 +815,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         int st;
         if (mode == SEARCH_RADIUS) st = k <= 32 ? launch_tile<32, 32, 2, SEARCH_RADIUS>(grid.view, a, stream) : launch_tile<64, 32, 4, SEARCH_RADIUS>(grid.view, a, stream);
         else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
-        else if (k <= 52) st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
+        else if (k <= tile_wide_k()) st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
         else st = launch_tile<64, 64>(grid.view, a, stream);
         if (st == PGEOF_OK && want_stats) {
             unsigned long long h[ST_N];
