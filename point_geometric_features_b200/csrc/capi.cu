@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <map>
+#include <chrono>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -53,41 +54,74 @@ KernelTimer::~KernelTimer()
 }
 
 // ---------------------------------------------------------------------------
-// device scratch: cudaMallocAsync on the device's default pool, never trimmed
+// device scratch: caching arena (see DeviceBuffer in common.cuh)
 // ---------------------------------------------------------------------------
-static std::mutex g_pool_mutex;
-static bool g_pool_ready[64] = {};
+struct ArenaBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t event; };
+struct DeviceArena {
+    std::mutex m;
+    std::multimap<size_t, ArenaBlock> free_blocks[64];
+    static size_t round(size_t b) { const size_t g = b < ((size_t)1 << 20) ? 512 : ((size_t)2 << 20); return (b + g - 1) / g * g; }
+    void trim_locked(int dev)
+    {
+        for (auto& kv : free_blocks[dev]) { cudaFree(kv.second.ptr); if (kv.second.event) cudaEventDestroy(kv.second.event); }
+        free_blocks[dev].clear();
+    }
+};
+static DeviceArena& arena() { static DeviceArena* a = new DeviceArena(); return *a; }   // leaked on purpose (exit order)
 
-static int ensure_pool(int device)
-{
-    std::lock_guard<std::mutex> lock(g_pool_mutex);
-    if (device < 0 || device >= 64 || g_pool_ready[device]) return PGEOF_OK;
-    cudaMemPool_t pool;
-    PGEOF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t keep = UINT64_MAX;
-    PGEOF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    g_pool_ready[device] = true;
-    return PGEOF_OK;
-}
+static int ensure_pool(int) { return PGEOF_OK; }
 
-int DeviceBuffer::alloc(size_t bytes, cudaStream_t s)
+int DeviceBuffer::alloc(size_t want_bytes, cudaStream_t s)
 {
     release();
-    stream = s;
-    if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(&ptr, bytes, s);
-    if (e != cudaSuccess) {
-        ptr = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); set_error("no current CUDA device"); return PGEOF_ECUDA; }
+    const size_t want = DeviceArena::round(want_bytes ? want_bytes : 16);
+    DeviceArena& ar = arena();
+    {
+        std::lock_guard<std::mutex> lock(ar.m);
+        auto& fl = ar.free_blocks[dev];
+        auto it = fl.lower_bound(want);
+        if (it != fl.end() && it->first <= want + want / 4 + ((size_t)1 << 20)) {
+            const ArenaBlock blk = it->second;
+            fl.erase(it);
+            // stream-ordered reuse: work queued on another stream before the release must be over first
+            if (blk.stream != s && blk.event && cudaStreamWaitEvent(s, blk.event, 0) != cudaSuccess) cudaGetLastError();
+            ptr = blk.ptr; bytes = blk.bytes; event = blk.event; stream = s; device = dev;
+            return PGEOF_OK;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {                       // give the cached blocks back and try once more
         cudaGetLastError();
-        set_error("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        cudaDeviceSynchronize();
+        { std::lock_guard<std::mutex> lock(ar.m); ar.trim_locked(dev); }
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
         return e == cudaErrorMemoryAllocation ? PGEOF_ENOMEM : PGEOF_ECUDA;
     }
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); ev = nullptr; }
+    ptr = p; bytes = want; event = ev; stream = s; device = dev;
     return PGEOF_OK;
 }
 
 void DeviceBuffer::release()
 {
-    if (ptr) { cudaFreeAsync(ptr, stream); ptr = nullptr; }
+    if (!ptr) return;
+    cudaEvent_t ev = (cudaEvent_t)event;
+    bool recorded = ev && cudaEventRecord(ev, stream) == cudaSuccess;
+    if (!recorded) { cudaGetLastError(); cudaStreamSynchronize(stream); }   // no event: make the block safe for any stream
+    DeviceArena& ar = arena();
+    {
+        std::lock_guard<std::mutex> lock(ar.m);
+        ar.free_blocks[device].emplace(bytes, ArenaBlock{ptr, bytes, recorded ? stream : nullptr, ev});
+    }
+    ptr = nullptr; bytes = 0; event = nullptr;
 }
 
 // ---------------------------------------------------------------------------
@@ -189,6 +223,34 @@ struct PinnedPool {
 };
 static PinnedPool& pinned_pool() { static PinnedPool* p = new PinnedPool(); return *p; }   // leaked on purpose (exit order)
 
+// PGEOF_HOST_TRACE=1: wall-clock of the phases of a host-buffer call (synchronises between phases; diagnostics only)
+struct HostTrace {
+    bool on;
+    cudaStream_t s;
+    const char* what;
+    std::chrono::steady_clock::time_point t0, t;
+    std::string line;
+    HostTrace(const char* w, cudaStream_t st) : on(std::getenv("PGEOF_HOST_TRACE") != nullptr), s(st), what(w)
+    {
+        if (on) t0 = t = std::chrono::steady_clock::now();
+    }
+    void mark(const char* phase)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        char buf[64];
+        std::snprintf(buf, sizeof(buf), " %s %.1f", phase, std::chrono::duration<double, std::milli>(now - t).count());
+        line += buf;
+        t = now;
+    }
+    ~HostTrace()
+    {
+        if (on) std::fprintf(stderr, "[pgeof host] %s:%s | total %.1f ms\n", what, line.c_str(),
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 // host <-> device staging helpers
 static int h2d(DeviceBuffer* d, const void* h, size_t bytes, cudaStream_t s)
 {
@@ -260,10 +322,11 @@ int pgeof_trim(void)
     }
     int dev = 0;
     if (ensure_device(&dev) != PGEOF_OK) return PGEOF_OK;
-    cudaMemPool_t pool;
     PGEOF_CUDA(cudaDeviceSynchronize());
-    PGEOF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    PGEOF_CUDA(cudaMemPoolTrimTo(pool, 0));
+    {
+        std::lock_guard<std::mutex> lock(arena().m);
+        arena().trim_locked(dev);
+    }
     return PGEOF_OK;
 }
 
@@ -319,6 +382,7 @@ int pgeof_knn_search(const float* data, size_t n_data, const float* query, size_
     PGEOF_TRY(host_stream(&s));
     if (n_query == 0 || knn == 0) return PGEOF_OK;
     PGEOF_REQUIRE(data && query && indices && sqr_dist, "null pointer argument");
+    HostTrace trace("knn_search", s);
     DeviceBuffer d_data, d_query, d_idx, d_d2;
     PGEOF_TRY(h2d(&d_data, data, n_data * 12, s));
     const bool self = (query == data && n_query == n_data);
@@ -326,11 +390,15 @@ int pgeof_knn_search(const float* data, size_t n_data, const float* query, size_
     const size_t out_elems = n_query * (size_t)knn;
     PGEOF_TRY(d_idx.alloc(out_elems * 4, s));
     PGEOF_TRY(d_d2.alloc(out_elems * 4, s));
+    trace.mark("alloc+h2d");
     PGEOF_TRY(search_run(SEARCH_KNN, d_data.as<float>(), n_data, self ? d_data.as<float>() : d_query.as<float>(), n_query, knn, 0.f,
                          d_idx.ptr, d_d2.as<float>(), nullptr, s));
+    trace.mark("search");
     PGEOF_TRY(d2h(indices, d_idx, out_elems * 4, s));
+    trace.mark("d2h idx");
     PGEOF_TRY(d2h(sqr_dist, d_d2, out_elems * 4, s));
     PGEOF_CUDA(cudaStreamSynchronize(s));
+    trace.mark("d2h d2");
     return PGEOF_OK;
 }
 
@@ -482,11 +550,15 @@ int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, s
     PGEOF_TRY(host_stream(&s));
     if (n_rows == 0) return PGEOF_OK;
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    HostTrace trace("compute_features", s);
     CsrOnDevice d;
     PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * 11, s));
+    trace.mark("alloc+h2d");
     PGEOF_TRY(features_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_min, eig_order, d.out.as<float>(), s));
+    trace.mark("features");
     PGEOF_TRY(d2h(out, d.out, n_rows * 11 * 4, s));
     PGEOF_CUDA(cudaStreamSynchronize(s));
+    trace.mark("d2h");
     return PGEOF_OK;
 }
 

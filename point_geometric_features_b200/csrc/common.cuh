@@ -48,11 +48,16 @@ struct KernelTimer {
     ~KernelTimer();
 };
 
-// Stream-ordered device scratch from the device's default memory pool (kept cached:
-// the release threshold is raised to "never" on first use, see capi.cu).
+// Device scratch from the library's own caching arena (capi.cu): blocks are cudaMalloc'ed once, kept on a per-device
+// free list and handed out again by size.  A block released on stream A and reused on stream B waits for the event
+// recorded at its release, so reuse is stream ordered.  (The driver's cudaMallocAsync pool was measured to stall
+// 50-700 ms at random when 2 GB results and 40-160 MB temporaries alternate: profiles/r1c_summary.md.)
 struct DeviceBuffer {
     void* ptr = nullptr;
     cudaStream_t stream = nullptr;
+    size_t bytes = 0;         // capacity of the arena block
+    int device = -1;
+    void* event = nullptr;    // cudaEvent_t owned by the block
     DeviceBuffer() = default;
     DeviceBuffer(const DeviceBuffer&) = delete;
     DeviceBuffer& operator=(const DeviceBuffer&) = delete;
