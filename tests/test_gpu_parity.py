@@ -446,6 +446,15 @@ def test_slab_shards_reproduce_the_single_device_rows():
     assert bool(seen.all())
 
 
+def test_randomised_search_cases_against_brute_force():
+    """tools/fuzz_search.py for a few seconds: random cloud shapes / sizes / k / radius, query == data or not, checked
+    bit for bit against a brute-force evaluation of the defined metric on the device (2800 large cases ran clean in r1)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_search.py"), "8"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
 # --------------------------------------------------------------------------------------------
 # BASELINE full size (10M points, k = 50): size-independent properties + sampled oracle rows
 # --------------------------------------------------------------------------------------------
