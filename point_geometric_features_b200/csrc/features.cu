@@ -410,53 +410,56 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
     }
 }
 
-// compute_features_multiscale on the direct walker: 128 rows per CTA; every row's n_scales_pass x 11 block is
-// staged in shared memory (zeros where the row is too short, pgeof.hpp:193) and written as one contiguous run
-__global__ void __launch_bounds__(kRows, 8) multiscale_direct_kernel(const FeatArgs a)
+// compute_features_multiscale on the direct walker: 512 rows per CTA, no shared memory (all of it stays L1 for the
+// gathers); a row's 11 floats of a scale are stored straight from the thread when the walk reaches that prefix
+// length (44 contiguous bytes; rows too short for a scale get zeros, pgeof.hpp:175,193)
+constexpr int kMsThreads = 256;
+
+__device__ __forceinline__ void store11(float* dst, const float (&f)[11])
 {
-    extern __shared__ __align__(16) float s_ms[];                   // [kRows][n_scales_pass * 11]
-    __shared__ uint32_t s_rowid[kRows];
-    const uint32_t r0 = blockIdx.x * kRows, rows = min((uint32_t)kRows, a.n_rows - r0);
-    const uint32_t W = a.n_scales_pass * 11;
-    float* mine = s_ms + threadIdx.x * W;
-    for (uint32_t i = 0; i < W; ++i) mine[i] = 0.f;
-    uint32_t row = r0 + threadIdx.x;
-    if (threadIdx.x < rows && a.order) row = __ldg(a.order + row);
-    s_rowid[threadIdx.x] = row;
-    if (threadIdx.x < rows) {
-        const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
-        if (e < b || e > a.nnz) atomicExch(a.err, 1);
-        else {
-            const uint32_t len = e - b;
-            uint32_t n_fit = 0;                                     // scales of this pass the row is long enough for
-            while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
-            if (n_fit && a.scales[n_fit - 1] > 0) {
-                Moments m;
-                uint32_t s = 0;
-                while (s < n_fit && a.scales[s] == 0) ++s;           // k_s = 0 is rejected on the host; defensive
-                auto acc = [&](uint32_t j, float dx, float dy, float dz) {
-                    m.add(dx, dy, dz);
-                    while (s < n_fit && a.scales[s] == j + 1) {
-                        float f[11];
-                        features11<float>(m.pca(j + 1, a.eig_order), f);
 #pragma unroll
-                        for (int i = 0; i < 11; ++i) mine[s * 11 + i] = f[i];
+    for (int i = 0; i < 11; ++i) dst[i] = f[i];
+}
+
+// kept out of line: the walker inlines its accumulator at 22 sites, the eigen solve + 11 formulas are ~400 instructions
+__device__ __noinline__ void emit_scale(Moments m, uint32_t k, int eig_order, float* dst)
+{
+    float f[11];
+    features11<float>(m.pca(k, eig_order), f);
+    store11(dst, f);
+}
+
+__global__ void __launch_bounds__(kMsThreads, 3) multiscale_direct_kernel(const FeatArgs a)
+{
+    uint32_t row = blockIdx.x * kMsThreads + threadIdx.x;
+    if (row >= a.n_rows) return;
+    if (a.order) row = __ldg(a.order + row);
+    float* out = a.out + ((size_t)row * a.n_scales_total + a.scale_base) * 11;
+    const float zero[11] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+    uint32_t n_fit = 0, s = 0;                                  // scales of this pass the row is long enough for / written so far
+    if (e < b || e > a.nnz) atomicExch(a.err, 1);
+    else {
+        const uint32_t len = e - b;
+        while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
+        if (n_fit && a.scales[n_fit - 1] > 0) {
+            Moments m;
+            while (s < n_fit && a.scales[s] == 0) { store11(out + s * 11, zero); ++s; }   // k_s = 0 is rejected on the host; defensive
+            uint32_t next_k = s < n_fit ? a.scales[s] : 0xffffffffu;      // prefix length of the next scale to emit (register, not a.scales[s])
+            auto acc = [&](uint32_t j, float dx, float dy, float dz) {
+                m.add(dx, dy, dz);
+                if (j + 1 == next_k) {
+                    do {
+                        emit_scale(m, j + 1, a.eig_order, out + s * 11);
                         ++s;
-                    }
-                };
-                if (!walk_direct<0>(a, b, a.scales[n_fit - 1], acc)) {
-                    atomicExch(a.err, 2);
-                    for (uint32_t i = 0; i < W; ++i) mine[i] = 0.f;
+                        next_k = s < n_fit ? a.scales[s] : 0xffffffffu;
+                    } while (next_k == j + 1);
                 }
-            }
+            };
+            if (!walk_direct<0>(a, b, a.scales[n_fit - 1], acc)) { atomicExch(a.err, 2); s = 0; }
         }
     }
-    __syncthreads();
-    const size_t stride = (size_t)a.n_scales_total * 11;
-    for (uint32_t i = threadIdx.x; i < rows * W; i += kRows) {
-        const uint32_t r = i / W, f = i - r * W;
-        a.out[(size_t)s_rowid[r] * stride + (size_t)a.scale_base * 11 + f] = s_ms[i];
-    }
+    for (; s < a.n_scales_pass; ++s) store11(out + s * 11, zero);
 }
 
 // out[row] = tmp[inv[row]]: undoes the spatial row permutation with random 4F-byte READS and fully coalesced
@@ -846,7 +849,11 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
         a.n_scales_pass = (uint32_t)std::min<size_t>(kMaxScalesPerPass, n_scales - base);
         for (uint32_t s = 0; s < a.n_scales_pass; ++s) a.scales[s] = k_scales_host[base + s];
         if (env_int("PGEOF_FEATURES_LAYOUT", 1) == 0) PGEOF_TRY(launch_tiles(multiscale_kernel, "multiscale", a, fixed + (size_t)a.nn_cap * 4, stream));
-        else PGEOF_TRY(launch_tiles(multiscale_direct_kernel, "multiscale", a, (size_t)kRows * a.n_scales_pass * 11 * sizeof(float), stream));
+        else {
+            KernelTimer timer("multiscale", stream);
+            multiscale_direct_kernel<<<(unsigned)((n_rows + kMsThreads - 1) / kMsThreads), kMsThreads, 0, stream>>>(a);
+            PGEOF_LAUNCH_CHECK();
+        }
     }
     return device_flag_check(err.as<int>(), stream, "compute_features_multiscale");
 }
