@@ -112,6 +112,38 @@ __device__ __forceinline__ Pca<T> pca_from_cov(T a00, T a01, T a02, T a11, T a12
     return r;
 }
 
+// Eigenvalues only, float, cyclic Jacobi without the eigenvector accumulation: backward stable, every eigenvalue is
+// within a few ulp of the matrix NORM (also when eigenvalues coincide or vanish, where the closed-form trigonometric
+// solution loses half the digits).  Used as the FILTER of the optimal-k scan; unsorted, clamped at 0.
+__device__ __forceinline__ void jacobi_eigvals_f32(float a00, float a01, float a02, float a11, float a12, float a22, float (&w)[3])
+{
+    float scale = fmaxf(fmaxf(fabsf(a00), fabsf(a11)), fabsf(a22));
+    scale = fmaxf(scale, fmaxf(fmaxf(fabsf(a01), fabsf(a02)), fabsf(a12)));
+    if (!(scale > 0.f)) { w[0] = w[1] = w[2] = 0.f; return; }
+    const float inv = 1.f / scale;
+    a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
+#define PGEOF_ROT(app, aqq, apq, arp, arq)                                            \
+    if (apq != 0.f) {                                                                 \
+        const float theta = (aqq - app) / (2.f * apq);                                \
+        float t = 1.f / (fabsf(theta) + sqrtf(theta * theta + 1.f));                  \
+        if (theta < 0.f) t = -t;                                                      \
+        const float c = rsqrtf(t * t + 1.f), sn = t * c;                              \
+        app -= t * apq; aqq += t * apq; apq = 0.f;                                    \
+        const float rp = arp, rq = arq;                                               \
+        arp = c * rp - sn * rq; arq = sn * rp + c * rq;                               \
+    }
+#pragma unroll 1
+    for (int sweep = 0; sweep < 6; ++sweep) {
+        const float off = fabsf(a01) + fabsf(a02) + fabsf(a12);
+        if (off <= 1e-8f * (fabsf(a00) + fabsf(a11) + fabsf(a22))) break;
+        PGEOF_ROT(a00, a11, a01, a02, a12)
+        PGEOF_ROT(a00, a22, a02, a01, a12)
+        PGEOF_ROT(a11, a22, a12, a01, a02)
+    }
+#undef PGEOF_ROT
+    w[0] = fmaxf(a00 * scale, 0.f); w[1] = fmaxf(a11 * scale, 0.f); w[2] = fmaxf(a22 * scale, 0.f);
+}
+
 // include/pca.hpp:140-150
 template <typename T>
 __device__ __forceinline__ T eigentropy_of(T l0, T l1, T l2)

@@ -462,6 +462,101 @@ __global__ void __launch_bounds__(kMsThreads, 3) multiscale_direct_kernel(const 
     for (; s < a.n_scales_pass; ++s) store11(out + s * 11, zero);
 }
 
+// compute_features_optimal on the direct walker.  Prefix moments in double as in optimal_kernel; the entropy of every
+// candidate size is first evaluated in FLOAT from Jacobi eigenvalues (accurate to a few ulp of the matrix norm for
+// every eigenvalue, so the float and double entropies differ by < 3e-5 in the worst case, ~1e-6 typically).  A
+// candidate that wins or loses by more than kOptMargin is decided by the float values; anything closer is decided by
+// the double values exactly as the all-double scan does (strict '<', smallest k wins ties, pgeof.hpp:289), so the
+// chosen k is identical.  The evaluation is kept out of line: the walker inlines its accumulator at 22 sites.
+constexpr float kOptMargin = 2e-4f;
+
+struct OptState {
+    double best_c[6];
+    double best_h64;
+    float best_h32;
+    uint32_t best_k;
+    int have64;
+};
+
+__device__ __forceinline__ double entropy_f64(const double (&c)[6])
+{
+    double w[3];
+    eigvals3_f64(c[0], c[1], c[2], c[3], c[4], c[5], w);
+    return eigentropy_of<double>(w[0], w[1], w[2]);
+}
+
+__device__ __noinline__ void optimal_eval(MomentsD m, uint32_t k, int first, OptState* st)
+{
+    double c[6];
+    m.cov(k, c);
+    float w[3];
+    jacobi_eigvals_f32((float)c[0], (float)c[1], (float)c[2], (float)c[3], (float)c[4], (float)c[5], w);
+    const float h32 = eigentropy_of<float>(w[0], w[1], w[2]);
+    bool take = first || h32 < st->best_h32 - kOptMargin;
+    int exact = 0;
+    double h64 = 0.0;
+    if (!take && !(h32 > st->best_h32 + kOptMargin)) {                      // too close to call in float
+        if (!st->have64) { st->best_h64 = entropy_f64(st->best_c); st->have64 = 1; }
+        h64 = entropy_f64(c);
+        take = h64 < st->best_h64;                                          // pgeof.hpp:289
+        exact = 1;
+    }
+    if (take) {
+        st->best_k = k; st->best_h32 = h32; st->best_h64 = h64; st->have64 = exact;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) st->best_c[i] = c[i];
+    }
+}
+
+__global__ void __launch_bounds__(kRows, 4) optimal_direct_kernel(const FeatArgs a)
+{
+    __shared__ uint32_t s_rowid[kRows];
+    __shared__ float s_out[kRows * 12];
+    const uint32_t r0 = blockIdx.x * kRows;
+    Tile t{r0, min((uint32_t)kRows, a.n_rows - r0), a.order == nullptr};
+    float f[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) f[i] = 0.f;
+    uint32_t row = r0 + threadIdx.x;
+    if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
+    s_rowid[threadIdx.x] = row;
+    if (threadIdx.x < t.rows) {
+        const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+        if (e < b || e > a.nnz) atomicExch(a.err, 1);
+        else {
+            const uint32_t len = e - b;
+            if (len >= a.k_min && len >= a.k_min_search && len > 0) {                     // pgeof.hpp:272
+                const uint32_t k0 = min(max(max(a.k_min, a.k_min_search), 1u), len);    // :274
+                MomentsD m;
+                OptState st;
+                st.best_k = len; st.best_h32 = 0.f; st.best_h64 = 0.0; st.have64 = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) st.best_c[i] = 0.0;
+                uint32_t rem = 0;                                                        // k % k_step, kept incrementally
+                auto acc = [&](uint32_t j, float dx, float dy, float dz) {
+                    m.add((double)dx, (double)dy, (double)dz);
+                    const uint32_t k = j + 1;
+                    rem = rem + 1 == a.k_step ? 0u : rem + 1;
+                    if (k < k0 || (k > k0 && rem != 0 && k != len)) return;              // :283
+                    optimal_eval(m, k, k == k0, &st);
+                };
+                if (!walk_direct<0>(a, b, len, acc)) atomicExch(a.err, 2);
+                else {
+                    float g[11];
+                    features11<float>(pca_from_cov<float>((float)st.best_c[0], (float)st.best_c[1], (float)st.best_c[2], (float)st.best_c[3],
+                                                         (float)st.best_c[4], (float)st.best_c[5], a.eig_order), g);
+#pragma unroll
+                    for (int i = 0; i < 11; ++i) f[i] = g[i];
+                    f[11] = (float)st.best_k;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s_out[threadIdx.x * 12 + i] = f[i];
+    store_rows<12>(a, t, s_out, s_rowid);
+}
+
 // out[row] = tmp[inv[row]]: undoes the spatial row permutation with random 4F-byte READS and fully coalesced
 // writes (scattered 44-B row writes from the feature kernel cost more than the whole neighbourhood walk:
 // partial-sector writes, profiles/r1f)
@@ -873,9 +968,11 @@ int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, siz
     PGEOF_TRY(prepare(&a, &pre, stream));
     const size_t fixed = Smem<12>::kNn;
     a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
-    // (an FP32 pre-filter of the 91 candidate sizes was tried and dropped: the closed-form eigenvalues lose ~1e-3 in float
-    // when two eigenvalues nearly coincide, which no fixed margin covers; the scan stays in double)
-    PGEOF_TRY(launch_tiles(optimal_kernel, "optimal", a, fixed + (size_t)a.nn_cap * 4, stream));
+    // layout 1: float Jacobi filter + double recheck of near ties on the direct walker; layout 0: all-double scan over a
+    // shared-memory nn tile.  (A float CLOSED-FORM filter was tried first and dropped: it loses ~1e-3 when two
+    // eigenvalues nearly coincide, which no fixed margin covers.)
+    if (env_int("PGEOF_FEATURES_LAYOUT", 1) == 0) PGEOF_TRY(launch_tiles(optimal_kernel, "optimal", a, fixed + (size_t)a.nn_cap * 4, stream));
+    else PGEOF_TRY(launch_tiles(optimal_direct_kernel, "optimal", a, 0, stream));
     return device_flag_check(err.as<int>(), stream, "compute_features_optimal");
 }
 
