@@ -5,7 +5,7 @@
 // 64-bit (d2, index) key threshold, and the cell coverage of a ball is computed with directed
 // rounding, see search_core.cuh):
 //
-//  * knn_tile_kernel (kNN, k <= 64): ONE THREAD PER QUERY, one warp per 32 consecutive queries of
+//  * knn_tile_kernel (kNN and padded radius search, k / max_knn <= 64): ONE THREAD PER QUERY, one warp per 32 consecutive queries of
 //    the cell-sorted order.  The 32 queries of a warp live in one (y, z) cell row, so they share one
 //    candidate region: the cells that intersect the warp's query bounding box dilated by the
 //    search radius R (R seeded from the local density), staged in shared memory by one 1-D TMA
@@ -289,7 +289,7 @@ struct TileCfg {
     static constexpr int LCAP = NLOAD + 1 + SINK;  // list entries per lane
     static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
     static constexpr int WARPS = NWARPS;
-    static constexpr int CMAX = NLOAD <= 96 ? 872 : 1016;  // candidates staged per pass (16 B each), multiple of 8 (k > 52: balls of ~90 points need ~800)
+    static constexpr int CMAX = 872;               // candidates staged per pass (16 B each), multiple of 8
     static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
     static constexpr int STAGE_BYTES = CMAX * 16;
     static constexpr int BAR_BYTES = 16 + 3 * 128;   // mbarrier + three per-lane words kept out of the register file (see below)
@@ -749,9 +749,9 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 // survivors the tile kernel's sorting network absorbs for a given k
 float env_float(const char* name, float dflt);
 
-// largest k served by the 96-key network; above it (up to 64) the 128-key one
-inline uint32_t tile_wide_k() { return (uint32_t)env_float("PGEOF_KNN_WIDE_K", 64.f); }
-inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= tile_wide_k() ? 96 : 128); }
+// survivors the tile kernel's sorting network absorbs for a given k (a 128-key network for 52 < k <= 64 was
+// measured slower than this one at every k: 6 instead of 8 resident warps, 1342 instead of 985 comparators)
+inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : 96; }
 
 template <int MODE>
 int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, cudaStream_t stream)
@@ -815,8 +815,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         int st;
         if (mode == SEARCH_RADIUS) st = k <= 32 ? launch_tile<32, 32, 2, SEARCH_RADIUS>(grid.view, a, stream) : launch_tile<64, 32, 4, SEARCH_RADIUS>(grid.view, a, stream);
         else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
-        else if (k <= tile_wide_k()) st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
-        else st = launch_tile<64, 64>(grid.view, a, stream);
+        else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
         if (st == PGEOF_OK && want_stats) {
             unsigned long long h[ST_N];
             PGEOF_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
