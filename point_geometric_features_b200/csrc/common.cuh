@@ -82,6 +82,11 @@ struct GridView {
     float slack;          // bound on |nominal cell boundary - true assignment boundary|
     int n[3];             // cells per axis
     uint32_t n_pts;
+    // A grid built for queries that live in a small part of the cloud indexes only the points inside [clip_lo, clip_hi]
+    // (the query bounding box dilated by rmax_safe, cut to the cloud's bounding box): a search is exact on it as long as
+    // its ball radius stays <= rmax_safe.  The full grid has clip = +-FLT_MAX and rmax_safe = +inf.
+    float clip_lo[3], clip_hi[3];
+    float rmax_safe;
     const uint32_t* cell_start;   // [n_cells + 1]
     const float4* pts;            // [n_pts] (x, y, z, bits(original index)), sorted by cell
 };
@@ -96,7 +101,17 @@ struct Grid {
 // from `target_occupancy` (mean points per h^3 of the bounding box).  Cells are `x_refine`
 // times finer along x (the contiguous axis), which costs nothing at query time: a query
 // still reads one contiguous span per (y, z) row, only trimmed more tightly.
-int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, int x_refine, cudaStream_t stream, Grid* out);
+struct GridClip {
+    float lo[3], hi[3];   // index only the points inside this box (already cut to the cloud's bounding box)
+    float cell_edge;      // first guess of the (y, z) cell edge, from the density of the whole cloud
+    float rmax_safe;      // ball radius up to which a search of a query inside the undilated box sees every point it needs
+};
+int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, int x_refine, cudaStream_t stream, Grid* out,
+               const GridClip* clip = nullptr);
+
+// bounding boxes of one or two (n,3) clouds with a single host synchronisation; false if a cloud holds non-finite values
+int bbox_host(const float* a, size_t na, const float* b, size_t nb, cudaStream_t stream, float (&alo)[3], float (&ahi)[3],
+              float (&blo)[3], float (&bhi)[3]);
 
 // Sorts `query` (device, (nq,3)) by the cell of `grid` it falls in (clamped) and
 // returns float4 (x, y, z, bits(original index)) records in that order.

@@ -49,13 +49,23 @@ __global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict_
 }
 
 // Histogram with warp-aggregated atomics.  rank[i] = position of point i inside its cell.
+__device__ __forceinline__ bool inside_clip(const GridView& g, float x, float y, float z)
+{
+    return x >= g.clip_lo[0] && x <= g.clip_hi[0] && y >= g.clip_lo[1] && y <= g.clip_hi[1] && z >= g.clip_lo[2] && z <= g.clip_hi[2];
+}
+
+// use_clip: points outside the grid's clip box are not indexed (data); queries are always kept
 __global__ void __launch_bounds__(kThreads) cell_count_kernel(GridView g, const float* __restrict__ xyz, size_t n,
-                                                              uint32_t* __restrict__ counts, uint32_t* __restrict__ rank)
+                                                              uint32_t* __restrict__ counts, uint32_t* __restrict__ rank, int use_clip)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
+    bool valid = i < n;
     uint32_t cid = 0xffffffffu;
-    if (valid) cid = cell_index(g, __ldg(xyz + 3 * i), __ldg(xyz + 3 * i + 1), __ldg(xyz + 3 * i + 2));
+    if (valid) {
+        const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+        valid = !use_clip || inside_clip(g, x, y, z);
+        if (valid) cid = cell_index(g, x, y, z);
+    }
     const unsigned active = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const unsigned peers = __match_any_sync(active, cid);
@@ -69,25 +79,27 @@ __global__ void __launch_bounds__(kThreads) cell_count_kernel(GridView g, const 
 
 // sum of c^2 over the cell counts: sum c^2 / n is the occupancy of the cell an average POINT lives in.  Uniform data:
 // mean occupancy + 1; a cloud of surfaces / clusters in a mostly empty bounding box: orders of magnitude more.
-__global__ void __launch_bounds__(kThreads) occupancy_kernel(const uint32_t* __restrict__ counts, size_t n_cells, unsigned long long* __restrict__ sum_sq)
+__global__ void __launch_bounds__(kThreads) occupancy_kernel(const uint32_t* __restrict__ counts, size_t n_cells, unsigned long long* __restrict__ sums)
 {
-    unsigned long long acc = 0;
+    unsigned long long acc = 0, cnt = 0;    // sums[0] = sum c^2, sums[1] = sum c (points indexed: < n on a clipped grid)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (size_t)gridDim.x * blockDim.x) {
         const unsigned long long c = __ldg(counts + i);
         acc += c * c;
+        cnt += c;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(sum_sq, acc);
+    for (int o = 16; o > 0; o >>= 1) { acc += __shfl_xor_sync(0xffffffffu, acc, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(sums, acc); atomicAdd(sums + 1, cnt); }
 }
 
 __global__ void __launch_bounds__(kThreads) scatter_kernel(GridView g, const float* __restrict__ xyz, size_t n,
                                                            const uint32_t* __restrict__ cell_start,
-                                                           const uint32_t* __restrict__ rank, float4* __restrict__ out)
+                                                           const uint32_t* __restrict__ rank, float4* __restrict__ out, int use_clip)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    if (use_clip && !inside_clip(g, x, y, z)) return;
     const uint32_t cid = cell_index(g, x, y, z);
     const uint32_t pos = __ldg(cell_start + cid) + __ldg(rank + i);
     out[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)i));
@@ -197,6 +209,35 @@ int exclusive_scan_u32(uint32_t* data, size_t n, cudaStream_t stream)
     return PGEOF_OK;
 }
 
+static int reduce_bbox(const float* hp, float (&lo)[3], float (&hi)[3])
+{
+    for (int d = 0; d < 3; ++d) { lo[d] = FLT_MAX; hi[d] = -FLT_MAX; }
+    for (int b = 0; b < kBBoxBlocks; ++b)
+        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], hp[b * 6 + d]); hi[d] = std::max(hi[d], hp[b * 6 + 3 + d]); }
+    for (int d = 0; d < 3; ++d)
+        if (!(lo[d] <= hi[d]) || !std::isfinite(lo[d]) || !std::isfinite(hi[d])) { set_error("point cloud holds non-finite coordinates"); return PGEOF_EINVAL; }
+    return PGEOF_OK;
+}
+
+int bbox_host(const float* a, size_t na, const float* b, size_t nb, cudaStream_t stream, float (&alo)[3], float (&ahi)[3],
+              float (&blo)[3], float (&bhi)[3])
+{
+    DeviceBuffer partial;
+    PGEOF_TRY(partial.alloc(2 * kBBoxBlocks * 6 * sizeof(float), stream));
+    bbox_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(a, na, partial.as<float>());
+    PGEOF_LAUNCH_CHECK();
+    if (b) {
+        bbox_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(b, nb, partial.as<float>() + kBBoxBlocks * 6);
+        PGEOF_LAUNCH_CHECK();
+    }
+    static thread_local float hp[2 * kBBoxBlocks * 6];
+    PGEOF_CUDA(cudaMemcpyAsync(hp, partial.ptr, (b ? 2 : 1) * kBBoxBlocks * 6 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    PGEOF_CUDA(cudaStreamSynchronize(stream));
+    PGEOF_TRY(reduce_bbox(hp, alo, ahi));
+    if (b) PGEOF_TRY(reduce_bbox(hp + kBBoxBlocks * 6, blo, bhi));
+    return PGEOF_OK;
+}
+
 static size_t max_cells_for(size_t n)
 {
     // the dense cell table costs 12 B of scan traffic per cell; keep it comparable to the point data
@@ -205,26 +246,21 @@ static size_t max_cells_for(size_t n)
     return std::min<size_t>(cap, (size_t)1 << 28);
 }
 
-int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, int x_refine, cudaStream_t stream, Grid* out)
+int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupancy, int x_refine, cudaStream_t stream, Grid* out,
+               const GridClip* clip)
 {
     if (n == 0 || n > 0xfffffff0ull) { set_error("grid_build: n=%zu out of range", n); return PGEOF_EINVAL; }
     KernelTimer timer("grid_build", stream);
-    // 1. bounding box
-    DeviceBuffer partial;
-    PGEOF_TRY(partial.alloc(kBBoxBlocks * 6 * sizeof(float), stream));
-    bbox_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(xyz, n, partial.as<float>());
-    PGEOF_LAUNCH_CHECK();
-    float hp[kBBoxBlocks * 6];
-    PGEOF_CUDA(cudaMemcpyAsync(hp, partial.ptr, sizeof(hp), cudaMemcpyDeviceToHost, stream));
-    PGEOF_CUDA(cudaStreamSynchronize(stream));
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int b = 0; b < kBBoxBlocks; ++b)
-        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], hp[b * 6 + d]); hi[d] = std::max(hi[d], hp[b * 6 + 3 + d]); }
+    // 1. bounding box (of the clip box when the caller restricts the index; it already knows the cloud's)
+    float lo[3], hi[3];
+    if (clip) {
+        for (int d = 0; d < 3; ++d) { lo[d] = clip->lo[d]; hi[d] = clip->hi[d]; }
+    } else {
+        float qlo[3], qhi[3];
+        PGEOF_TRY(bbox_host(xyz, n, nullptr, 0, stream, lo, hi, qlo, qhi));
+    }
     double ext[3], maxabs = 0;
     for (int d = 0; d < 3; ++d) {
-        if (!(lo[d] <= hi[d]) || !std::isfinite(lo[d]) || !std::isfinite(hi[d])) {
-            set_error("point cloud holds non-finite coordinates"); return PGEOF_EINVAL;
-        }
         ext[d] = (double)hi[d] - (double)lo[d];
         maxabs = std::max(maxabs, std::max(std::fabs((double)lo[d]), std::fabs((double)hi[d])));
     }
@@ -232,9 +268,12 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
     double h = cell_edge;
     const bool adaptive = !(h > 0);
     if (adaptive) {
-        double vol = 1; int dims = 0;
-        for (int d = 0; d < 3; ++d) if (ext[d] > 0) { vol *= ext[d]; ++dims; }
-        h = dims ? std::pow(vol * std::max(1.0f, target_occupancy) / (double)n, 1.0 / dims) : 1.0;
+        if (clip) h = clip->cell_edge;     // density of the whole cloud (the number of points inside the box is not known yet)
+        else {
+            double vol = 1; int dims = 0;
+            for (int d = 0; d < 3; ++d) if (ext[d] > 0) { vol *= ext[d]; ++dims; }
+            h = dims ? std::pow(vol * std::max(1.0f, target_occupancy) / (double)n, 1.0 / dims) : 1.0;
+        }
     }
     const size_t cap = max_cells_for(n);
     GridView& g = out->view;
@@ -266,24 +305,26 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
         g.xf = xf;
         g.slack = (float)((2.0 * maxabs + h) * 9.5367431640625e-7);   // 2^-20
         g.n_pts = (uint32_t)n;
+        for (int d = 0; d < 3; ++d) { g.clip_lo[d] = clip ? clip->lo[d] : -FLT_MAX; g.clip_hi[d] = clip ? clip->hi[d] : FLT_MAX; }
+        g.rmax_safe = clip ? clip->rmax_safe : INFINITY;
         out->n_cells = (size_t)nc[0] * nc[1] * nc[2];
         // 3. histogram
         PGEOF_TRY(out->cell_start.alloc((out->n_cells + 1) * sizeof(uint32_t), stream));
         cs = out->cell_start.as<uint32_t>();
         PGEOF_CUDA(cudaMemsetAsync(cs, 0, (out->n_cells + 1) * sizeof(uint32_t), stream));
-        cell_count_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>());
+        cell_count_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), clip ? 1 : 0);
         PGEOF_LAUNCH_CHECK();
         if (!adaptive || attempt >= 2) break;
         // 3b. the edge above assumes the points fill their bounding box.  If the cell an average point lives in is far
         // fuller than intended (surfaces / clusters in a mostly empty box), shrink the cells and count again.
-        if (!stat.ptr) PGEOF_TRY(stat.alloc(sizeof(unsigned long long), stream));
-        PGEOF_CUDA(cudaMemsetAsync(stat.ptr, 0, sizeof(unsigned long long), stream));
+        if (!stat.ptr) PGEOF_TRY(stat.alloc(2 * sizeof(unsigned long long), stream));
+        PGEOF_CUDA(cudaMemsetAsync(stat.ptr, 0, 2 * sizeof(unsigned long long), stream));
         occupancy_kernel<<<kBBoxBlocks, kThreads, 0, stream>>>(cs, out->n_cells, stat.as<unsigned long long>());
         PGEOF_LAUNCH_CHECK();
-        unsigned long long sum_sq = 0;
-        PGEOF_CUDA(cudaMemcpyAsync(&sum_sq, stat.ptr, sizeof(sum_sq), cudaMemcpyDeviceToHost, stream));
+        unsigned long long sums[2] = {0, 0};
+        PGEOF_CUDA(cudaMemcpyAsync(sums, stat.ptr, sizeof(sums), cudaMemcpyDeviceToHost, stream));
         PGEOF_CUDA(cudaStreamSynchronize(stream));
-        const double seen = (double)sum_sq / (double)n;                                  // occupancy seen by a point (x-refined cells)
+        const double seen = (double)sums[0] / (double)std::max<unsigned long long>(sums[1], 1);                                  // occupancy seen by a point (x-refined cells)
         const double want = std::max(1.0f, target_occupancy) / xf + 1.0;                  // uniform data: mean + 1
         if (seen <= 2.5 * want || out->n_cells * 2 > cap) break;
         h *= std::max(0.25, std::pow(want / seen, 1.0 / 2.5));                            // between a surface (1/2) and a volume (1/3)
@@ -291,7 +332,7 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
     // 4. scan -> scatter
     PGEOF_TRY(out->pts.alloc(n * sizeof(float4), stream));
     PGEOF_TRY(exclusive_scan_u32(cs, out->n_cells, stream));
-    scatter_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), out->pts.as<float4>());
+    scatter_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), out->pts.as<float4>(), clip ? 1 : 0);
     PGEOF_LAUNCH_CHECK();
     g.cell_start = cs;
     g.pts = out->pts.as<float4>();
@@ -307,10 +348,10 @@ int grid_sort_queries(const Grid& grid, const float* query, size_t nq, cudaStrea
     PGEOF_TRY(rank.alloc(nq * sizeof(uint32_t), stream));
     PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, (grid.n_cells + 1) * sizeof(uint32_t), stream));
     const unsigned blocks = (unsigned)((nq + kThreads - 1) / kThreads);
-    cell_count_kernel<<<blocks, kThreads, 0, stream>>>(grid.view, query, nq, counts.as<uint32_t>(), rank.as<uint32_t>());
+    cell_count_kernel<<<blocks, kThreads, 0, stream>>>(grid.view, query, nq, counts.as<uint32_t>(), rank.as<uint32_t>(), 0);
     PGEOF_LAUNCH_CHECK();
     PGEOF_TRY(exclusive_scan_u32(counts.as<uint32_t>(), grid.n_cells, stream));
-    scatter_kernel<<<blocks, kThreads, 0, stream>>>(grid.view, query, nq, counts.as<uint32_t>(), rank.as<uint32_t>(), out->as<float4>());
+    scatter_kernel<<<blocks, kThreads, 0, stream>>>(grid.view, query, nq, counts.as<uint32_t>(), rank.as<uint32_t>(), out->as<float4>(), 0);
     PGEOF_LAUNCH_CHECK();
     return PGEOF_OK;
 }

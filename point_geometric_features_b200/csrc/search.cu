@@ -65,6 +65,8 @@ struct SearchArgs {
     uint32_t flags;          // debugging switches (PGEOF_KNN_FLAGS): 1 = volume-only radius seed, 2 = no radius retries
     uint2* slow_list;        // tile kernel: (query position, bits(radius hint)) of the queries left to knn_slow_kernel
     uint32_t* slow_count;
+    uint2* unsafe_list;      // clipped grid: queries whose ball outgrew GridView::rmax_safe (re-run on the full grid)
+    uint32_t* unsafe_count;
 };
 
 // tile-kernel counters: why queries left the fast path, and how much work the fast path did
@@ -75,7 +77,7 @@ enum { ST_SHORT = 0, ST_OVER, ST_TIE, ST_REGION, ST_FIXED, ST_PASSES, ST_CANDS, 
 // ---------------------------------------------------------------------------------------
 template <int CAP>
 __device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, float qy, float qz, uint32_t k, float target,
-                                                u64* keybuf, int lane, u64* tau_out, float r_hint = 0.f)
+                                                u64* keybuf, int lane, u64* tau_out, float r_hint = 0.f, bool* unsafe = nullptr)
 {
     float R = r_hint;
     if (!(r_hint > 0.f)) {   // no hint (warp uniform): seed the ball from the density of the 3x3x3 block
@@ -91,6 +93,9 @@ __device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, flo
     u64 tau = tau_from_radius(R);
     uint32_t c = 0;
     for (int it = 0; it < 512; ++it) {
+        // a clipped grid (GridView::rmax_safe) only holds what balls up to that radius need: leave, the caller re-runs
+        // the query on the full grid
+        if (Rg > g.rmax_safe) { if (unsafe) *unsafe = true; *tau_out = 0; return 0; }
         c = scan_ball<CAP, true>(g, qx, qy, qz, Rg, tau, keybuf, lane);
         if (c < k) {
             tau_lo = tau; have_lo = true;
@@ -362,6 +367,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 
     unsigned remaining = __ballot_sync(kFull, valid);
     unsigned slow = 0;                       // lanes finished by the generic routine
+    unsigned unsafe = 0;                     // lanes whose ball outgrew a clipped grid
     // per-lane state that lives across passes sits in shared memory: the sorting network leaves no register to spare
     float* const s_hint = reinterpret_cast<float*>(bar + 2) + lane;   // radius the generic routine starts from (0: local density)
     // feedback for data the uniform-density seed misjudges (surfaces, lines, clusters): lanes whose ball held too few /
@@ -439,6 +445,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 R = exp2f(lr) * rm;
             }
 
+            if (R > g.rmax_safe) { unsafe |= active; active = 0; break; }   // clipped grid: not every point of this ball is indexed
             // candidate region: cells meeting the dilated box; one contiguous span per (y, z) row
             const int cx0 = cell_coord(__fsub_rd(xmin, R), g.lo[0], g.inv_hx, g.n[0]);
             const int cx1 = cell_coord(__fadd_ru(xmax, R), g.lo[0], g.inv_hx, g.n[0]);
@@ -688,6 +695,12 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         at = __shfl_sync(kFull, at, 0);
         if ((slow >> lane) & 1u) a.slow_list[at + __popc(slow & lanemask_lt())] = make_uint2(base + lane, __float_as_uint(*s_hint));
     }
+    if (unsafe) {
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(a.unsafe_count, (uint32_t)__popc(unsafe));
+        at = __shfl_sync(kFull, at, 0);
+        if ((unsafe >> lane) & 1u) a.unsafe_list[at + __popc(unsafe & lanemask_lt())] = make_uint2(base + lane, 0u);
+    }
 }
 
 // generic per-query routine (one warp per query) over the queries the tile kernel queued
@@ -703,7 +716,12 @@ __global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g,
         const uint2 rec = a.slow_list[w];
         const float4 q4 = __ldg(a.queries + rec.x);
         u64 tau;
-        const uint32_t c = knn_collect<CAP>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, __uint_as_float(rec.y));
+        bool unsafe = false;
+        const uint32_t c = knn_collect<CAP>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, __uint_as_float(rec.y), &unsafe);
+        if (unsafe) {   // warp uniform
+            if (lane == 0) a.unsafe_list[atomicAdd(a.unsafe_count, 1u)] = make_uint2(rec.x, 0u);
+            continue;
+        }
         u64 v[M];
         select_and_sort<NOUT, CAP>(keybuf, c, tau, k, lane, v);
         write_knn_row<M>(a, __float_as_uint(q4.w), k, v, lane);
@@ -781,30 +799,68 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     Grid grid;
     float target = 0.f;
     const bool tile = (mode == SEARCH_KNN ? env_float("PGEOF_KNN_TILE", 1.f) != 0.f : mode == SEARCH_RADIUS && env_float("PGEOF_RADIUS_TILE", 1.f) != 0.f) && k <= 64;
+    if (mode != SEARCH_KNN && (!(radius >= 0.f) || !std::isfinite(radius))) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
+    float occ = 0.f, edge = 0.f;
+    int xf = 1;
     if (mode == SEARCH_KNN) {
         // ball seeded to hold k + z sigma + 2 points.  Tile path: z balances the two ways a query leaves the
         // fast path (fewer than k survivors / more than the sorting network absorbs); cell edge h slightly
-        // above that ball's radius so that a warp's region is 3 x 3 (y, z) rows, cells 4x finer along x.
+        // above that ball's radius so that a warp's region is 3 x 3 (y, z) rows, cells 8x finer along x.
         target = (float)k + (tile ? env_float("PGEOF_KNN_Z", 2.6f) : 2.f) * std::sqrt((float)k) + 2.f;
         if (tile) target = std::min(target, 0.5f * (float)(k + tile_nload(k)));
-        const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", tile ? 0.28f : 0.25f));
-        PGEOF_TRY(grid_build(data, n_data, 0.f, occ, tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1, stream, &grid));
+        occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", tile ? 0.28f : 0.25f));
+        xf = tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1;
     } else {
-        if (!(radius >= 0.f) || !std::isfinite(radius)) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
         // tile path: cell edge just above the radius, so that the ball of a query reaches one cell row to either side
-        const float edge = radius * env_float("PGEOF_RADIUS_CELL_SCALE", tile ? 1.002f : 1.0f);
-        PGEOF_TRY(grid_build(data, n_data, edge > 0.f ? edge : 1.f, 0.f, tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1, stream, &grid));
+        edge = radius * env_float("PGEOF_RADIUS_CELL_SCALE", tile ? 1.002f : 1.0f);
+        if (!(edge > 0.f)) edge = 1.f;
+        xf = tile ? (int)env_float("PGEOF_KNN_XF", 8.f) : 1;
     }
+    // Queries that live in a small part of the cloud (a spatial shard of a multi-GPU run, a region of interest): index only
+    // the points within `halo` of their bounding box.  Exact as long as no ball outgrows the halo; the kernels check
+    // that (GridView::rmax_safe) and hand the few queries that do to a second run on the full grid.
+    GridClip clip{};
+    bool clipped = false;
+    const bool sub_query = !(query == data && n_query == n_data);
+    if (sub_query && n_query * 2 <= n_data && (mode != SEARCH_KNN || tile) && env_float("PGEOF_GRID_CLIP", 1.f) != 0.f) {
+        float dlo[3], dhi[3], qlo[3], qhi[3];
+        PGEOF_TRY(bbox_host(data, n_data, query, n_query, stream, dlo, dhi, qlo, qhi));
+        double vol = 1, h_est = edge;
+        int dims = 0;
+        for (int d = 0; d < 3; ++d) if (dhi[d] > dlo[d]) { vol *= (double)dhi[d] - (double)dlo[d]; ++dims; }
+        if (mode == SEARCH_KNN) h_est = dims ? std::pow(vol * occ / (double)n_data, 1.0 / dims) : 1.0;
+        const float halo = mode == SEARCH_KNN ? 3.f * (float)h_est : 2.2f * radius + 1e-30f;
+        double cvol = 1;
+        bool any_cut = false;
+        for (int d = 0; d < 3; ++d) {
+            clip.lo[d] = std::max(dlo[d], std::nextafter(qlo[d] - halo, -INFINITY));
+            clip.hi[d] = std::min(dhi[d], std::nextafter(qhi[d] + halo, INFINITY));
+            if (clip.lo[d] > clip.hi[d]) { clip.lo[d] = dlo[d]; clip.hi[d] = dhi[d]; }   // queries outside the cloud on this axis
+            any_cut = any_cut || clip.lo[d] > dlo[d] || clip.hi[d] < dhi[d];
+            if (dhi[d] > dlo[d]) cvol *= std::max((double)clip.hi[d] - (double)clip.lo[d], 0.0) / ((double)dhi[d] - (double)dlo[d]);
+        }
+        bool inside = true;    // the exactness argument needs every query inside the undilated box: true by construction,
+        for (int d = 0; d < 3; ++d) inside = inside && qlo[d] >= dlo[d] - halo && qhi[d] <= dhi[d] + halo;   // except far outside the cloud
+        if (any_cut && inside && cvol < 0.6) {
+            clip.cell_edge = (float)h_est;
+            clip.rmax_safe = halo;
+            clipped = true;
+        }
+    }
+    PGEOF_TRY(grid_build(data, n_data, mode == SEARCH_KNN ? 0.f : edge, occ, xf, stream, &grid, clipped ? &clip : nullptr));
     DeviceBuffer qsorted;
     const float4* qrec;
     if (query == data && n_query == n_data) qrec = grid.view.pts;   // self query: reuse the sorted cloud
     else { PGEOF_TRY(grid_sort_queries(grid, query, n_query, stream, &qsorted)); qrec = qsorted.as<float4>(); }
-    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr, (uint32_t)env_float("PGEOF_KNN_FLAGS", 0.f), nullptr, nullptr};
+    SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr, (uint32_t)env_float("PGEOF_KNN_FLAGS", 0.f),
+                 nullptr, nullptr, nullptr, nullptr};
     if (tile) {
         DeviceBuffer stats, slow;
-        PGEOF_TRY(slow.alloc(16 + n_query * sizeof(uint2), stream));
+        PGEOF_TRY(slow.alloc(16 + (clipped ? 2 : 1) * n_query * sizeof(uint2), stream));
         a.slow_count = slow.as<uint32_t>();
         a.slow_list = reinterpret_cast<uint2*>(slow.as<unsigned char>() + 16);
+        a.unsafe_count = a.slow_count + 1;
+        a.unsafe_list = a.slow_list + (clipped ? n_query : 0);   // never written on a full grid (rmax_safe = +inf)
         PGEOF_CUDA(cudaMemsetAsync(a.slow_count, 0, 16, stream));
         const bool want_stats = env_float("PGEOF_KNN_STATS", 0.f) != 0.f;
         if (want_stats) {
@@ -816,6 +872,21 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         if (mode == SEARCH_RADIUS) st = k <= 32 ? launch_tile<32, 32, 2, SEARCH_RADIUS>(grid.view, a, stream) : launch_tile<64, 32, 4, SEARCH_RADIUS>(grid.view, a, stream);
         else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
         else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
+        uint32_t n_unsafe = 0;
+        if (st == PGEOF_OK && clipped && mode == SEARCH_KNN) {
+            PGEOF_CUDA(cudaMemcpyAsync(&n_unsafe, a.unsafe_count, sizeof(n_unsafe), cudaMemcpyDeviceToHost, stream));
+            PGEOF_CUDA(cudaStreamSynchronize(stream));
+            if (n_unsafe) {   // balls that outgrew the halo: the same generic routine over those queries on the FULL grid
+                Grid full;
+                PGEOF_TRY(grid_build(data, n_data, 0.f, occ, xf, stream, &full));
+                SearchArgs b = a;
+                b.slow_list = a.unsafe_list;
+                b.slow_count = a.unsafe_count;
+                if (k <= 32) knn_slow_kernel<32><<<148 * 4, kWarps * 32, 0, stream>>>(full.view, b);
+                else knn_slow_kernel<64><<<148 * 4, kWarps * 32, 0, stream>>>(full.view, b);
+                PGEOF_LAUNCH_CHECK();
+            }
+        }
         if (st == PGEOF_OK && want_stats) {
             unsigned long long h[ST_N];
             PGEOF_CUDA(cudaMemcpyAsync(h, stats.ptr, sizeof(h), cudaMemcpyDeviceToHost, stream));
@@ -823,6 +894,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
             uint32_t n_slow = 0;
             PGEOF_CUDA(cudaMemcpyAsync(&n_slow, a.slow_count, sizeof(n_slow), cudaMemcpyDeviceToHost, stream));
             PGEOF_CUDA(cudaStreamSynchronize(stream));
+            std::fprintf(stderr, "[pgeof knn tile] clipped grid=%d (halo %.3g) re-run on the full grid=%u\n", (int)clipped, clipped ? clip.rmax_safe : 0.f, n_unsafe);
             std::fprintf(stderr, "[pgeof knn tile] n=%zu k=%u target=%.1f h=%.3f: generic queries=%u | per-pass events: short=%llu over=%llu tie=%llu region=%llu "
                          "fixed rows=%llu passes=%llu candidates/pass=%.1f survivors/query=%.1f\n", n_query, k, target, grid.view.h, n_slow,
                          h[ST_SHORT], h[ST_OVER], h[ST_TIE], h[ST_REGION], h[ST_FIXED], h[ST_PASSES],

@@ -446,6 +446,25 @@ def test_slab_shards_reproduce_the_single_device_rows():
     assert bool(seen.all())
 
 
+def test_local_queries_use_a_clipped_grid_and_fall_back_when_a_ball_outgrows_it():
+    """Queries confined to a small box make the library index only the neighbourhood of that box (GridClip).  Queries in
+    a dense part stay on the clipped grid; queries inside an empty hole need balls far larger than the halo and must
+    be re-run on the full grid.  Both have to match the oracle bit for bit."""
+    rng = np.random.default_rng(41)
+    xyz = rng.uniform(0, 100, (300000, 3)).astype(np.float32)
+    hole = np.linalg.norm(xyz - np.float32([50, 50, 50]), axis=1) < 30
+    data = xyz[~hole]
+    in_hole = (np.float32([50, 50, 50]) + rng.uniform(-4, 4, (700, 3))).astype(np.float32)        # nearest data ~26 away
+    dense = data[(np.abs(data - np.float32([12, 12, 12])) < 6).all(1)][:3000]                     # a corner blob of data points
+    for k in (8, 50):
+        for q in (in_hole, dense, np.concatenate([in_hole[:50], dense[:50]])):
+            _assert_search_equal(pgeof.knn_search(data, q, k), cpu.knn_search(data, q, k, brute=True))
+    ridx, rd2 = pgeof.radius_search(data, dense, 1.5, 40)
+    ref = cpu.radius_search(data, dense, 1.5, 40)
+    np.testing.assert_array_equal(ridx, ref[0])
+    np.testing.assert_array_equal(rd2, ref[1])
+
+
 def test_randomised_search_cases_against_brute_force():
     """tools/fuzz_search.py for a few seconds: random cloud shapes / sizes / k / radius, query == data or not, checked
     bit for bit against a brute-force evaluation of the defined metric on the device (2800 large cases ran clean in r1)."""

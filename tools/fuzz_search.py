@@ -53,12 +53,31 @@ def main():
         xyz = cloud(rng, n, kind).astype(np.float32)
         n = len(xyz)
         data = torch.from_numpy(xyz).to(dev)
-        if rng.random() < 0.5:
-            query, sel = data, None
-        else:
+        u = rng.random()
+        if u < 0.35:
+            query = data
+        elif u < 0.6:
             m = int(rng.integers(1, min(n, 5000) + 1))
             qn = xyz[rng.integers(0, n, m)] + rng.normal(0, 0.05, (m, 3)).astype(np.float32) * (rng.random() < 0.7)
             query = torch.from_numpy(qn.astype(np.float32)).to(dev)
+        else:
+            # spatially local queries (a slab / a blob of the cloud, sometimes pushed partly outside it): the library then
+            # indexes only the neighbourhood of the query box and must hand balls that outgrow it to the full grid
+            ax = int(rng.integers(0, 3))
+            c = xyz[:, ax]
+            lo, hi = np.quantile(c, sorted(rng.uniform(0, 1, 2)))
+            sel = np.nonzero((c >= lo) & (c <= hi))[0]
+            if rng.random() < 0.5 and len(sel):
+                ctr = xyz[rng.choice(sel)]
+                d = np.linalg.norm(xyz - ctr, axis=1)
+                sel = np.argsort(d)[: max(1, int(rng.integers(1, max(2, n // 10))))]
+            if len(sel) == 0:
+                sel = np.arange(min(n, 10))
+            sel = sel[: n // 2] if n >= 4 else sel
+            qn = xyz[sel].copy()
+            if rng.random() < 0.3:
+                qn += rng.normal(0, 1, 3).astype(np.float32) * float(np.ptp(xyz, axis=0).max()) * float(rng.choice([0.01, 0.3, 2.0]))
+            query = torch.from_numpy(np.ascontiguousarray(qn, dtype=np.float32)).to(dev)
         rows = torch.from_numpy(rng.choice(query.shape[0], min(query.shape[0], 1500), replace=False)).to(dev)
         k = int(min(n, rng.choice([1, 2, 5, 16, 20, 31, 32, 33, 50, 52, 53, 60, 64, 65, 100])))
         idx, d2 = pgeof.knn_search(data, query, k)
