@@ -822,7 +822,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     GridClip clip{};
     bool clipped = false;
     const bool sub_query = !(query == data && n_query == n_data);
-    if (sub_query && n_query * 2 <= n_data && (mode != SEARCH_KNN || tile) && env_float("PGEOF_GRID_CLIP", 1.f) != 0.f) {
+    if (sub_query && n_query * 4 <= n_data * 3 && (mode != SEARCH_KNN || tile) && env_float("PGEOF_GRID_CLIP", 1.f) != 0.f) {
         float dlo[3], dhi[3], qlo[3], qhi[3];
         PGEOF_TRY(bbox_host(data, n_data, query, n_query, stream, dlo, dhi, qlo, qhi));
         double vol = 1, h_est = edge;
