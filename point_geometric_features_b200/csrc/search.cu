@@ -1,27 +1,32 @@
 // search.cu -- knn_search / radius_search on the uniform grid.
 // Replaces nanoflann_knn_search / nanoflann_radius_search (include/nn_search.hpp:31-132).
 //
-// Two kernels share the grid and the exactness argument (a point is only ever rejected by the
+// The kernels share the grid and the exactness argument (a point is only ever rejected by the
 // 64-bit (d2, index) key threshold, and the cell coverage of a ball is computed with directed
 // rounding, see search_core.cuh):
 //
-//  * knn_tile_kernel (kNN and padded radius search, k / max_knn <= 64): ONE THREAD PER QUERY, one warp per 32 consecutive queries of
-//    the cell-sorted order.  The 32 queries of a warp live in one (y, z) cell row, so they share one
+//  * knn_tile_kernel (kNN and padded radius search, k / max_knn <= 64): ONE THREAD PER QUERY, one warp per
+//    32 consecutive queries of the cell-sorted order.  The 32 queries of a warp live in one (y, z) cell row, so they share one
 //    candidate region: the cells that intersect the warp's query bounding box dilated by the
-//    search radius R (R seeded from the local density), staged in shared memory by one 1-D TMA
-//    bulk copy per cell row.  Every candidate is read ONCE per warp (a warp-uniform 128-bit
+//    search radius R (kNN: seeded from the density and shape of the 3 x 3 block of cell rows; radius
+//    search: given), staged in shared memory by one 1-D TMA bulk copy per cell row.  Every candidate is read ONCE per warp (a warp-uniform 128-bit
 //    load) and tested by the 32 lanes against their own query -- no ballots, shuffles or partially
 //    filled 32-candidate chunks in the inner loop.  Survivors (d2 <= fl(0.9999 R^2)) are appended
 //    to a per-lane shared-memory list as 32-bit words (22 bits of d2 | staged slot); the scan uses the
 //    FMA-contracted distance (6 instead of 8 FP32 instructions per candidate), every distance that is
 //    returned or decides an order is recomputed with the defined, non-contracted formula.  Each lane
 //    then loads its list into registers and runs a min/max sorting network that leaves the 64
-//    smallest of up to 96 (128) words in order; the exact (d2, index) pairs are rebuilt from the
+//    smallest of up to 96 words in order; the exact (d2, index) pairs are rebuilt from the
 //    staged candidates in that order, rows whose truncated keys collided are repaired by an
 //    insertion sort on the exact order, and the rows are written coalesced through a
 //    shared-memory transpose.  Lanes whose ball held fewer than k points, overflowed the network
-//    or hit a truncated-distance tie between the k-th neighbour and a dropped key are finished by
-//    the generic per-query routine inside the same kernel.
+//    or hit a truncated-distance tie between the k-th neighbour and a dropped key are queued for
+//    knn_slow_kernel / search_list_kernel (the generic per-query routine, one warp per queued query);
+//    half a warp failing the same way is re-queued as a group with a corrected radius instead.
+//
+//  * Clipped grids: when the queries of a call occupy a small box of the cloud, search_run indexes only
+//    the points within a halo of that box; every ball radius is checked against GridView::rmax_safe and
+//    the queries that exceed it are re-run on the full grid.
 //
 //  * search_kernel (kNN with 64 < k <= 512, radius modes): one warp per query.  Per query:
 //    (1) seed a radius from the local density of the 3x3x3 cell block, (2) scan the cells that
