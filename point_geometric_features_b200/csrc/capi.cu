@@ -663,6 +663,11 @@ int pgeof_knn_features_dev(const float* xyz, size_t n, uint32_t knn, uint32_t k_
     DeviceGuard guard;
     PGEOF_TRY(guard.enter(xyz));
     cudaStream_t s = (cudaStream_t)stream;
+    if (!indices && !sqr_dist) {     // nobody wants the neighbour lists: never materialise them
+        int done = 0;
+        PGEOF_TRY(knn_features_fused_run(xyz, n, knn, k_min, eig_order, features, s, &done));
+        if (done) return PGEOF_OK;
+    }
     DeviceBuffer t_idx, t_d2, ptr;
     if (!indices) { PGEOF_TRY(t_idx.alloc(n * (size_t)knn * 4, s)); indices = t_idx.as<uint32_t>(); }
     if (!sqr_dist) { PGEOF_TRY(t_d2.alloc(n * (size_t)knn * 4, s)); sqr_dist = t_d2.as<float>(); }

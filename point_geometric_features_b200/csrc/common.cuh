@@ -126,7 +126,10 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
                float radius, void* indices, float* sqr_dist, uint32_t* nn_ptr, cudaStream_t stream);
 
 int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
-                 uint32_t k_min, int eig_order, float* out, cudaStream_t stream);
+                 uint32_t k_min, int eig_order, float* out, cudaStream_t stream, const uint32_t* out_rows = nullptr);
+// knn_search(xyz, xyz, knn) + compute_features without materialising the neighbour lists (fused knn_features extension);
+// *done = 0 if the fused path declined (the caller then runs the two kernels)
+int knn_features_fused_run(const float* xyz, size_t n, uint32_t knn, uint32_t k_min, int eig_order, float* features, cudaStream_t stream, int* done);
 int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
                             size_t n_rows, const uint32_t* k_scales_host, size_t n_scales, int eig_order, float* out,
                             cudaStream_t stream);

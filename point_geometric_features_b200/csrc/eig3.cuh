@@ -144,6 +144,25 @@ __device__ __forceinline__ void jacobi_eigvals_f32(float a00, float a01, float a
     w[0] = fmaxf(a00 * scale, 0.f); w[1] = fmaxf(a11 * scale, 0.f); w[2] = fmaxf(a22 * scale, 0.f);
 }
 
+// origin-shifted first and second moments of a neighbourhood (shared by the feature kernels and the fused knn_features path)
+struct Moments {
+    float sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    __device__ __forceinline__ void add(float dx, float dy, float dz)
+    {
+        sx += dx; sy += dy; sz += dz;
+        sxx = fmaf(dx, dx, sxx); sxy = fmaf(dx, dy, sxy); sxz = fmaf(dx, dz, sxz);
+        syy = fmaf(dy, dy, syy); syz = fmaf(dy, dz, syz); szz = fmaf(dz, dz, szz);
+    }
+    // population covariance of the first k points (pca.hpp:75-76), shift invariant
+    __device__ __forceinline__ Pca<float> pca(uint32_t k, int eig_order) const
+    {
+        const float inv = 1.f / (float)k;
+        const float mx = sx * inv, my = sy * inv, mz = sz * inv;
+        return pca_from_cov<float>(fmaf(-mx, mx, sxx * inv), fmaf(-mx, my, sxy * inv), fmaf(-mx, mz, sxz * inv),
+                                   fmaf(-my, my, syy * inv), fmaf(-my, mz, syz * inv), fmaf(-mz, mz, szz * inv), eig_order);
+    }
+};
+
 // include/pca.hpp:140-150
 template <typename T>
 __device__ __forceinline__ T eigentropy_of(T l0, T l1, T l2)

@@ -50,28 +50,11 @@ struct FeatArgs {
     uint32_t nn_cap;       // entries of `nn` the shared-memory tile can hold
     int tma_in, tma_out;   // pointer alignment allows bulk copies
     int out_by_position;   // direct kernel: `out` is indexed by position in the row sequence (un-permuted by a second pass)
+    const uint32_t* out_rows;   // optional: CSR row r is written to out[out_rows[r]] (rows of a compact sub-problem, fused knn_features)
     // multiscale
     uint32_t scales[kMaxScalesPerPass]; uint32_t n_scales_pass; uint32_t n_scales_total; uint32_t scale_base;
     // optimal
     uint32_t k_step, k_min_search;
-};
-
-struct Moments {
-    float sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
-    __device__ __forceinline__ void add(float dx, float dy, float dz)
-    {
-        sx += dx; sy += dy; sz += dz;
-        sxx = fmaf(dx, dx, sxx); sxy = fmaf(dx, dy, sxy); sxz = fmaf(dx, dz, sxz);
-        syy = fmaf(dy, dy, syy); syz = fmaf(dy, dz, syz); szz = fmaf(dz, dz, szz);
-    }
-    // population covariance of the first k points (pca.hpp:75-76), shift invariant
-    __device__ __forceinline__ Pca<float> pca(uint32_t k, int eig_order) const
-    {
-        const float inv = 1.f / (float)k;
-        const float mx = sx * inv, my = sy * inv, mz = sz * inv;
-        return pca_from_cov<float>(fmaf(-mx, mx, sxx * inv), fmaf(-mx, my, sxy * inv), fmaf(-mx, mz, sxz * inv),
-                                   fmaf(-my, my, syy * inv), fmaf(-my, mz, syz * inv), fmaf(-mz, mz, szz * inv), eig_order);
-    }
 };
 
 struct MomentsD {
@@ -386,13 +369,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
     for (uint32_t tile = blockIdx.x * per; tile < t_end; ++tile) {
         const uint32_t r0 = tile * THREADS;
         // out_by_position: a.out is indexed by POSITION in the (permuted) row sequence, the tile's output is one contiguous block
-        Tile t{r0, min((uint32_t)THREADS, a.n_rows - r0), a.order == nullptr || a.out_by_position != 0};
+        Tile t{r0, min((uint32_t)THREADS, a.n_rows - r0), (a.order == nullptr && a.out_rows == nullptr) || a.out_by_position != 0};
         float f[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) f[i] = 0.f;
         uint32_t row = r0 + threadIdx.x;
         if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
-        s_rowid[threadIdx.x] = a.out_by_position ? r0 + threadIdx.x : row;
+        s_rowid[threadIdx.x] = a.out_by_position ? r0 + threadIdx.x : ((a.out_rows && threadIdx.x < t.rows) ? __ldg(a.out_rows + row) : row);
         if (threadIdx.x < t.rows) {
             const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
             if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
@@ -865,7 +848,7 @@ int device_flag_check(const int* d_flag, cudaStream_t stream, const char* what)
 }
 
 int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
-                 uint32_t k_min, int eig_order, float* out, cudaStream_t stream)
+                 uint32_t k_min, int eig_order, float* out, cudaStream_t stream, const uint32_t* out_rows)
 {
     if (n_rows == 0) return PGEOF_OK;
     DeviceBuffer err;
@@ -874,9 +857,10 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
     FeatArgs a;
     PGEOF_TRY(make_args(&a, xyz, n_xyz, nn, nnz, nn_ptr, n_rows, eig_order, out, err.as<int>(), 11));
     a.k_min = k_min;
+    a.out_rows = out_rows;
     Prepass pre;
     PGEOF_TRY(prepare(&a, &pre, stream));
-    const int layout = env_int("PGEOF_FEATURES_LAYOUT", 1);   // 1: direct nn stream (default), 0: shared-memory nn tile
+    const int layout = out_rows ? 1 : env_int("PGEOF_FEATURES_LAYOUT", 1);   // 1: direct nn stream (default), 0: shared-memory nn tile
     if (layout == 0) {
         const size_t fixed = Smem<11>::kNn;
         a.nn_cap = pick_nn_cap(nnz, n_rows, fixed);
@@ -884,7 +868,7 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
     } else {
         // permuted rows: features land in a position-indexed scratch block, then one gather pass restores row order
         DeviceBuffer tmp;
-        const bool unpermute = a.order && env_int("PGEOF_FEATURES_UNPERMUTE", 0) != 0;   // measured: no gain over scattered row writes
+        const bool unpermute = a.order && !out_rows && env_int("PGEOF_FEATURES_UNPERMUTE", 0) != 0;   // measured: no gain over scattered row writes
         if (unpermute) {
             a.out_by_position = 1;
             PGEOF_TRY(tmp.alloc(n_rows * 11 * sizeof(float), stream));

@@ -41,6 +41,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "eig3.cuh"
 #include "ptx.cuh"
 #include "search_core.cuh"
 
@@ -72,6 +73,13 @@ struct SearchArgs {
     uint32_t* slow_count;
     uint2* unsafe_list;      // clipped grid: queries whose ball outgrew GridView::rmax_safe (re-run on the full grid)
     uint32_t* unsafe_count;
+    // fused knn_features: the tile kernel turns its rows straight into features, the generic kernel parks its rows
+    float* features;         // (n_query, 11) out
+    uint32_t k_min;
+    int eig_order;
+    uint32_t* tmp_idx;       // [tmp_cap][k] neighbour rows of the queries the tile kernel queued
+    uint32_t* tmp_rows;      // [tmp_cap] their row ids
+    uint32_t tmp_cap;
 };
 
 // tile-kernel counters: why queries left the fast path, and how much work the fast path did
@@ -342,10 +350,11 @@ __device__ __forceinline__ uint32_t select_sort_network(uint32_t (&v)[NOUT + NEX
     return dropped;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS, int MODE>
+template <int NOUT, int NEXTRA, int NWARPS, int MODE, bool FUSED = false>
 __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
 {
     static_assert(MODE == SEARCH_KNN || MODE == SEARCH_RADIUS, "tile kernel: kNN or padded radius search");
+    static_assert(!FUSED || MODE == SEARCH_KNN, "fused features: kNN only");
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     constexpr int M = NOUT / 32, NLOAD = Cfg::NLOAD, S = Cfg::STRIDE;
     extern __shared__ __align__(128) unsigned char smem_tile[];
@@ -601,12 +610,15 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 pd = d; pi = id;
                 if (MODE == SEARCH_RADIUS) nvalid += ((uint32_t)i < cnt && d < __float_as_uint(r2)) ? 1u : 0u;
                 plane_d[i * S] = d;
-                v[i] = id;
+                if (FUSED) reinterpret_cast<uint16_t*>(list + NOUT * S)[i * 32 + lane] = (uint16_t)(v[i] & Cfg::SLOT_MASK);
+                else v[i] = id;
             }
-            __syncwarp();                      // the staged candidates are dead: index plane
-            uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
+            if (!FUSED) {
+                __syncwarp();                  // the staged candidates are dead: index plane
+                uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
 #pragma unroll
-            for (int i = 0; i < NOUT; ++i) plane_i[i * S] = v[i];
+                for (int i = 0; i < NOUT; ++i) plane_i[i * S] = v[i];
+            }
         }
         {
             uint32_t* plane_d = list + lane;
@@ -614,7 +626,32 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             uint32_t any_bad = 0;
 #pragma unroll
             for (int r = 0; r < M; ++r) any_bad |= bad[r];
-            if (ok && any_bad) {
+            if (FUSED && ok && any_bad) {
+                // same repair on (d2, staged slot) pairs: the candidates stay staged, their index is read when two distances tie
+                uint16_t* pslot = reinterpret_cast<uint16_t*>(list + NOUT * S) + lane;
+                uint32_t first = 0, last = 0;
+#pragma unroll
+                for (int r = M - 1; r >= 0; --r) if (bad[r]) first = r * 32 + __ffs(bad[r]) - 1;
+#pragma unroll
+                for (int r = 0; r < M; ++r) if (bad[r]) last = r * 32 + 31 - __clz(bad[r]);
+                const uint32_t nfix = min(cnt, (uint32_t)NOUT);
+                for (uint32_t i = first; i < nfix; ++i) {
+                    const uint32_t d = plane_d[i * S];
+                    const uint16_t sl = pslot[i * 32];
+                    const uint32_t id = __float_as_uint(stage[sl].w);
+                    uint32_t j = i;
+                    while (j > 0) {
+                        const uint32_t qd = plane_d[(j - 1) * S];
+                        const uint16_t qs = pslot[(j - 1) * 32];
+                        if (qd < d || (qd == d && __float_as_uint(stage[qs].w) < id)) break;
+                        plane_d[j * S] = qd; pslot[j * 32] = qs;
+                        --j;
+                    }
+                    if (j != i) { plane_d[j * S] = d; pslot[j * 32] = sl; }
+                    else if (i > last) break;
+                }
+            }
+            if (!FUSED && ok && any_bad) {
                 // insertion sort on the exact (d2, index) order from the first inversion on; past the last
                 // inversion the first entry found in place ends it (everything behind it is in order already)
                 uint32_t first = 0, last = 0;
@@ -663,6 +700,36 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         }
         slow |= __ballot_sync(kFull, mine && !ok) & ~requeued;
         __syncwarp();
+        if (FUSED) {
+            // ---- fused knn_features: moments of the k nearest straight from the staged candidates, in the exact
+            // order compute_features would walk them (same origin, same operations: the result is bit identical),
+            // eigen solve + 11 formulas per lane, rows staged in shared memory and written as 44-byte runs
+            float f[11];
+#pragma unroll
+            for (int i = 0; i < 11; ++i) f[i] = 0.f;
+            if (ok && k >= a.k_min) {
+                const uint16_t* pslot = reinterpret_cast<const uint16_t*>(list + NOUT * S) + lane;
+                const float4 o = stage[pslot[0]];
+                Moments m;
+#pragma unroll 4
+                for (uint32_t i = 1; i < k; ++i) {
+                    const float4 p = stage[pslot[i * 32]];
+                    m.add(p.x - o.x, p.y - o.y, p.z - o.z);
+                }
+                features11<float>(m.pca(k, a.eig_order), f);
+            }
+            __syncwarp();                      // the planes are dead
+            float* s_feat = reinterpret_cast<float*>(list);
+#pragma unroll
+            for (int i = 0; i < 11; ++i) s_feat[lane * 11 + i] = f[i];
+            __syncwarp();
+            const unsigned okm = __ballot_sync(kFull, ok);
+#pragma unroll 4
+            for (int q = 0; q < 32; ++q) {
+                const uint32_t rowq = __shfl_sync(kFull, row, q);
+                if (((okm >> q) & 1u) && lane < 11) a.features[(size_t)rowq * 11 + lane] = s_feat[q * 11 + lane];
+            }
+        } else
         // ---- write the finished rows, one coalesced row at a time ---------------------------------
         {
             const uint32_t* plane_d = list;
@@ -729,7 +796,16 @@ __global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g,
         }
         u64 v[M];
         select_and_sort<NOUT, CAP>(keybuf, c, tau, k, lane, v);
-        write_knn_row<M>(a, __float_as_uint(q4.w), k, v, lane);
+        if (a.tmp_idx) {   // fused knn_features: park the row (indices only) for the feature pass over the queued queries
+            if (w < a.tmp_cap) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const uint32_t e = m * 32 + lane;
+                    if (e < k) a.tmp_idx[(size_t)w * k + e] = key_idx(v[m]);
+                }
+                if (lane == 0) a.tmp_rows[w] = __float_as_uint(q4.w);
+            }
+        } else write_knn_row<M>(a, __float_as_uint(q4.w), k, v, lane);
         __syncwarp();
     }
 }
@@ -750,12 +826,12 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN>
+template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN, bool FUSED = false>
 int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
-    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE>;
+    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE, FUSED>;
     PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
     {
@@ -786,6 +862,12 @@ int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, cudaStre
     if (k <= 512) return launch_search<512, MODE>(g, a, stream);
     set_error("knn / max_knn = %u exceeds the supported maximum of 512 neighbours per query", k);
     return PGEOF_EINVAL;
+}
+
+__global__ void iota_scale_u32(uint32_t* out, size_t n, uint32_t k)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)(i * k);
 }
 
 float env_float(const char* name, float dflt)
@@ -858,7 +940,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     if (query == data && n_query == n_data) qrec = grid.view.pts;   // self query: reuse the sorted cloud
     else { PGEOF_TRY(grid_sort_queries(grid, query, n_query, stream, &qsorted)); qrec = qsorted.as<float4>(); }
     SearchArgs a{qrec, (uint32_t)n_query, k, radius, target, indices, sqr_dist, nn_ptr, nullptr, (uint32_t)env_float("PGEOF_KNN_FLAGS", 0.f),
-                 nullptr, nullptr, nullptr, nullptr};
+                 nullptr, nullptr, nullptr, nullptr, nullptr, 1u, 0, nullptr, nullptr, 0u};
     if (tile) {
         DeviceBuffer stats, slow;
         PGEOF_TRY(slow.alloc(16 + (clipped ? 2 : 1) * n_query * sizeof(uint2), stream));
@@ -914,6 +996,48 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         case SEARCH_RADIUS_CSR: return dispatch_search<SEARCH_RADIUS_CSR>(k, grid.view, a, stream);
     }
     return PGEOF_EINVAL;
+}
+
+// Fused knn_features: knn_search(xyz, xyz, k) + compute_features without ever writing the (idx, d2) rows
+// or reading them back: the tile kernel accumulates the moments of the k nearest from its staged candidates.  The ~2 %
+// of the queries it queues go through the generic search into a compact scratch CSR and the ordinary feature kernel.
+int knn_features_fused_run(const float* xyz, size_t n, uint32_t k, uint32_t k_min, int eig_order, float* features, cudaStream_t stream, int* done)
+{
+    *done = 0;
+    if (n == 0 || k == 0 || k > 64 || n > 0xfffffff0ull || env_float("PGEOF_KNN_FUSED", 1.f) == 0.f) return PGEOF_OK;
+    float target = (float)k + env_float("PGEOF_KNN_Z", 2.6f) * std::sqrt((float)k) + 2.f;
+    target = std::min(target, 0.5f * (float)(k + tile_nload(k)));
+    const float occ = std::max(2.f, target * env_float("PGEOF_KNN_CELL_OCC", 0.28f));
+    Grid grid;
+    PGEOF_TRY(grid_build(xyz, n, 0.f, occ, (int)env_float("PGEOF_KNN_XF", 8.f), stream, &grid));
+    const uint32_t cap = (uint32_t)std::max<size_t>(n / 8, 4096);
+    DeviceBuffer slow, tmp_idx, tmp_rows;
+    PGEOF_TRY(slow.alloc(16 + n * sizeof(uint2), stream));
+    PGEOF_TRY(tmp_idx.alloc((size_t)cap * k * sizeof(uint32_t), stream));
+    PGEOF_TRY(tmp_rows.alloc((size_t)cap * sizeof(uint32_t), stream));
+    SearchArgs a{grid.view.pts, (uint32_t)n, k, 0.f, target, nullptr, nullptr, nullptr, nullptr, (uint32_t)env_float("PGEOF_KNN_FLAGS", 0.f),
+                 nullptr, nullptr, nullptr, nullptr, features, k_min, eig_order, tmp_idx.as<uint32_t>(), tmp_rows.as<uint32_t>(), cap};
+    a.slow_count = slow.as<uint32_t>();
+    a.slow_list = reinterpret_cast<uint2*>(slow.as<unsigned char>() + 16);
+    a.unsafe_count = a.slow_count + 1;
+    a.unsafe_list = a.slow_list;
+    PGEOF_CUDA(cudaMemsetAsync(a.slow_count, 0, 16, stream));
+    if (k <= 32) PGEOF_TRY((launch_tile<32, 32, 2, SEARCH_KNN, true>(grid.view, a, stream)));
+    else PGEOF_TRY((launch_tile<64, 32, 4, SEARCH_KNN, true>(grid.view, a, stream)));
+    uint32_t n_slow = 0;
+    PGEOF_CUDA(cudaMemcpyAsync(&n_slow, a.slow_count, sizeof(n_slow), cudaMemcpyDeviceToHost, stream));
+    PGEOF_CUDA(cudaStreamSynchronize(stream));
+    if (n_slow > cap) return PGEOF_OK;              // unusually many queued queries (very non-uniform data): the caller runs the two kernels
+    if (n_slow) {
+        DeviceBuffer ptr;
+        PGEOF_TRY(ptr.alloc(((size_t)n_slow + 1) * sizeof(uint32_t), stream));
+        iota_scale_u32<<<(n_slow + 1 + 255) / 256, 256, 0, stream>>>(ptr.as<uint32_t>(), (size_t)n_slow + 1, k);
+        PGEOF_LAUNCH_CHECK();
+        PGEOF_TRY(features_run(xyz, n, tmp_idx.as<uint32_t>(), (size_t)n_slow * k, ptr.as<uint32_t>(), n_slow, k_min, eig_order, features, stream,
+                               tmp_rows.as<uint32_t>()));
+    }
+    *done = 1;
+    return PGEOF_OK;
 }
 
 }  // namespace pgeof

@@ -465,6 +465,25 @@ def test_local_queries_use_a_clipped_grid_and_fall_back_when_a_ball_outgrows_it(
     np.testing.assert_array_equal(rd2, ref[1])
 
 
+@pytest.mark.parametrize("order", ORDERS)
+def test_fused_knn_features_is_bit_identical_to_the_two_calls(order):
+    """knn_features without return_neighbors never writes the (idx, d2) rows: the tile kernel accumulates the moments
+    from its staged candidates in the order compute_features walks them, so every row must match bit for bit --
+    uniform and LiDAR-like data (the latter sends a third of the queries through the generic search + feature pass)."""
+    import torch
+    b200.set_eig_order(order)
+    for xyz, k in ((synth.uniform_cloud(400000, seed=51), 50), (synth.uniform_cloud(60000, seed=52), 7),
+                   (synth.lidar_like_cloud(300000, seed=2), 32)):
+        t = torch.from_numpy(xyz).cuda()
+        idx, _ = pgeof.knn_search(t, t, k)
+        ptr = (torch.arange(len(xyz) + 1, device="cuda") * k).to(torch.uint32)
+        for k_min in (1, k + 1):
+            ref = pgeof.compute_features(t, idx.view(-1), ptr, k_min)
+            fused = b200.knn_features(t, k, k_min)
+            assert bool((fused.view(torch.int32) == ref.view(torch.int32)).all())
+    b200.set_eig_order("literal")
+
+
 def test_randomised_search_cases_against_brute_force():
     """tools/fuzz_search.py for a few seconds: random cloud shapes / sizes / k / radius, query == data or not, checked
     bit for bit against a brute-force evaluation of the defined metric on the device (2800 large cases ran clean in r1)."""
