@@ -27,4 +27,18 @@ pgeof.compute_features_selected(xyz, 0.4, 10, [pgeof.EFeatureID.Verticality, pge
 pgeof.compute_features_selected(xyz.astype(np.float64), 0.4, 10, [pgeof.EFeatureID.Verticality, pgeof.EFeatureID.Eigentropy])
 nn3, ptr3 = synth.knn_csr(idx)
 pgeof.compute_features(xyz, nn3, ptr3)
+# paths added in round 1: larger uniform cloud (tile kernel fast path + repairs), local queries on a clipped grid with
+# balls that outgrow it, padded radius search on the tile kernel, permuted feature rows, fused knn_features
+import torch  # noqa: E402
+big = synth.uniform_cloud(60000, seed=1)
+pgeof.knn_search(big, big, 50)
+pgeof.knn_search(big, big[(big[:, 2] > 80) & (big[:, 2] < 100)], 20)
+pgeof.knn_search(big, (np.float32([100, 100, 100]) + np.random.default_rng(1).uniform(-1, 1, (64, 3))).astype(np.float32), 64)
+pgeof.radius_search(big, big, 6.0, 40)
+i50, _ = pgeof.knn_search(big, big, 23)
+pgeof.compute_features(big, *synth.knn_csr(i50))
+t = torch.from_numpy(big).cuda()
+b200.knn_features(t, 50)
+b200.knn_features(t, 9, 1, True)
+torch.cuda.synchronize()
 print("sanitize_small ok")
