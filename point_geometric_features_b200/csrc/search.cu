@@ -319,6 +319,7 @@ struct TileCfg {
     // network, the slot finds the candidate again when the exact (d2, index) pair is rebuilt
     static constexpr uint32_t SLOT_BITS = 10;
     static constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1;
+    static constexpr uint32_t PAD = ~SLOT_MASK;    // key of an empty list position: above every real key (d2 bits of a NaN), slot 0
     static_assert(CMAX % 8 == 0 && CMAX <= (1 << SLOT_BITS), "slot field too small");
     static_assert(LIST_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "alignment");
     static_assert(NOUT * STRIDE * 4 <= LIST_BYTES && NOUT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 #pragma unroll
             for (int i = 0; i < NLOAD; ++i) {
                 const uint32_t w = wbase[i * S];
-                v[i] = (uint32_t)i < cnt ? w : 0xffffffffu;
+                v[i] = (uint32_t)i < cnt ? w : Cfg::PAD;   // sorts behind every real key, and its slot field (0) is a staged candidate
             }
             __syncwarp();                      // the lists are dead: their memory becomes the d2 plane
             dropped = select_sort_network<NOUT, NEXTRA>(v);
@@ -683,10 +684,10 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 // row must be full (k valid entries) and the dropped keys two buckets above its last entry, as in (a)
                 need = min(nvalid, k);
                 const uint32_t kth = plane_d[(max(need, 1u) - 1) * S];
-                tie = ok && dropped != 0xffffffffu && (need < k || (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u);
+                tie = ok && dropped < Cfg::PAD && (need < k || (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u);
             } else {
                 const uint32_t kth = plane_d[(k - 1) * S];
-                tie = ok && ((dropped != 0xffffffffu && (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u) ||
+                tie = ok && ((dropped < Cfg::PAD && (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u) ||
                              !(__uint_as_float(kth) <= t2_safe));
             }
             if (tie) ok = false;
