@@ -1,22 +1,23 @@
 #!/usr/bin/env python
 """Headline benchmark (BASELINE.json): points/s of knn_search(k=50) + compute_features on 10 M
-synthetic points, 1/2/4/8 B200.
+synthetic points, 1/2/4/8 B200 -- plus the other BASELINE.json configurations behind --config.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config M|C2|C3|C4|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One *step* = one pass of the hot path over the whole cloud:
+One *step* = one pass of the hot path over the whole cloud (config M, the metric):
     idx, d2 = knn_search(xyz, xyz[shard], 50); nn = idx.view(-1); nn_ptr = arange * 50;
     feats   = compute_features(xyz, nn, nn_ptr)
 `value`  : device-resident throughput (inputs already in HBM, CUDA events, max over ranks).
 `e2e`    : the same pipeline through the drop-in module with HOST (numpy, pinned) buffers --
            H2D / D2H copies inside the timed region.
-`roofline`: the dominant kernel's algorithmic bytes / its measured duration against the measured
-           HBM copy bandwidth (MEASURED_PEAKS.json).
+`roofline`: the dominant kernel's algorithmic bytes / its measured duration against the
+           measured HBM copy bandwidth (MEASURED_PEAKS.json); `traffic` from the tracked ncu summary
+           profiles/traffic.json (written by tools/ncu_traffic.py from an `ncu --set full` capture).
 `cpu_baseline` / `--impl reference`: the C++ restatement of the reference's CPU path (oracle/, kind
            "port": the reference itself is unbuildable here) on all host threads, bounded sample.
-Multi-GPU: the cloud is replicated, queries are sharded contiguously across ranks (strong scaling of
-the one 10 M cloud; no data-path collective), rank 0 prints ONE JSON line.
+Multi-GPU: the cloud is replicated, every rank owns a spatial slab of the queries (strong scaling of the
+one cloud; no data-path collective) in the device leg AND in the e2e leg, rank 0 prints ONE JSON line.
 """
 import argparse
 import json
@@ -31,8 +32,26 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "points/s: knn_search k=50 + compute_features, 10M pts"
 UNIT = "points/s"
+
+# BASELINE.json configs (C1 is the README example = a parity test, not a bench line)
+CONFIGS = {
+    "M": dict(points=10_000_000, cloud="uniform", search=("knn", 50), feat=("features",), cpu_sample=500_000,
+              metric="points/s: knn_search k=50 + compute_features, 10M pts",
+              workload="uniform [0,200)^3 float32 cloud (seed 0), knn_search(k=50) -> CSR view -> compute_features (11 features); grid build included in every step"),
+    "C2": dict(points=1_000_000, cloud="uniform", search=("knn", 50), feat=("features",), cpu_sample=500_000,
+               metric="points/s: knn_search k=50 + compute_features, 1M pts",
+               workload="BASELINE configs[1]: 1 M uniform points, knn_search(k=50) -> CSR view -> compute_features (11 features)"),
+    "C3": dict(points=10_000_000, cloud="lidar", search=("radius", 0.2, 64), feat=("features",), cpu_sample=300_000,
+               metric="points/s: radius_search r=0.2 max_k=64 -> CSR -> compute_features, 10M LiDAR-like pts",
+               workload="BASELINE configs[2]: 10 M LiDAR-like scene (ground / walls / poles / scatter, seed 0), radius_search r=0.2 max_k=64 emitted as CSR -> compute_features"),
+    "C4": dict(points=10_000_000, cloud="uniform", search=("knn", 100), feat=("multiscale", [10, 20, 50, 100]), cpu_sample=200_000,
+               metric="points/s: knn_search k=100 + compute_features_multiscale [10,20,50,100], 10M pts",
+               workload="BASELINE configs[3]: 10 M uniform points, one k=100 kNN pass -> compute_features_multiscale k_scales=[10,20,50,100]"),
+    "C5": dict(points=50_000_000, cloud="uniform", search=("knn", 100), feat=("optimal", 1, 1, 10), cpu_sample=100_000,
+               metric="points/s: knn_search k=100 + compute_features_optimal k_min_search=10..100 k_step=1, 50M pts",
+               workload="BASELINE configs[4]: 50 M uniform points, k=100 kNN -> compute_features_optimal(k_min_search=10, k_step=1), rows in shard-local CSR blocks of <= 2^32-1 neighbours"),
+}
 
 
 def parse():
@@ -41,14 +60,25 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--points", type=int, default=10_000_000)
-    p.add_argument("--knn", type=int, default=50)
+    p.add_argument("--config", default="M", choices=sorted(CONFIGS))
+    p.add_argument("--points", type=int, default=0, help="0 = the size the config names")
+    p.add_argument("--knn", type=int, default=0, help="0 = the k the config names")
     p.add_argument("--scaling", default="strong", choices=["strong", "weak"])
-    p.add_argument("--cpu-sample", type=int, default=500_000, help="points of the bounded CPU sample")
+    p.add_argument("--cpu-sample", type=int, default=0, help="points of the bounded CPU sample (0 = per config)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
-    return p.parse_args()
+    a = p.parse_args()
+    cfg = dict(CONFIGS[a.config])
+    if a.points:
+        cfg["points"] = a.points
+    if a.knn and cfg["search"][0] == "knn":
+        cfg["search"] = ("knn", a.knn)
+    if a.cpu_sample:
+        cfg["cpu_sample"] = a.cpu_sample
+    cfg["cpu_sample"] = min(cfg["cpu_sample"], cfg["points"])
+    a.cfg = cfg
+    return a
 
 
 def peaks():
@@ -56,6 +86,15 @@ def peaks():
     if os.path.exists(path):
         return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tracked_traffic():
+    """dram read + write bytes per row of the hot kernels, from the tracked summary of the latest `ncu --set full` capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)), "profiles/traffic.json"
+    except Exception:
+        return {}, None
 
 
 class ClockSampler:
@@ -132,19 +171,51 @@ class ClockSampler:
                 "samples": len(rows), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
-def sample_cloud(n_total, n_sample, seed=0):
-    """Bounded CPU sample of the same workload: a sub-cube of the uniform cloud at EQUAL density."""
-    from point_geometric_features_b200 import synth
-    extent = 200.0 * (n_sample / float(n_total)) ** (1.0 / 3.0)
-    return synth.uniform_cloud(n_sample, seed=seed, extent=extent)
+# ------------------------------------------------------------------------------------------------
+# synthetic clouds: pure numpy here, so that the CPU arms never map the product's shared libraries
+# ------------------------------------------------------------------------------------------------
+def load_synth():
+    """point_geometric_features_b200/synth.py loaded as a stand-alone module (numpy only): importing the package would
+    import the CUDA extension, which the reference arm must not touch."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_pgeof_synth", os.path.join(ROOT, "point_geometric_features_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
-def cpu_step(cpu, xyz, k):
+def make_cloud(synth, cfg, n, seed=0, n_total=None):
+    """The config's cloud at `n` points; a bounded sample (n < n_total) keeps the DENSITY of the full-size cloud."""
+    n_total = n_total or n
+    frac = n / float(n_total)
+    if cfg["cloud"] == "lidar":
+        return synth.lidar_like_cloud(n, seed=seed, extent=140.0 * frac ** 0.5)
+    return synth.uniform_cloud(n, seed=seed, extent=200.0 * frac ** (1.0 / 3.0))
+
+
+def cpu_step(cpu, cfg, xyz):
+    """The config's pipeline on the CPU port, float32 arithmetic as the reference, README glue included."""
     import numpy as np
-    idx, _ = cpu.knn_search(xyz, xyz, k)                       # KD-tree build + query, all host threads
-    nn_ptr = (np.arange(xyz.shape[0] + 1) * k).astype(np.uint32)   # README glue (README.md:135-141)
-    nn = idx.reshape(-1)
-    return cpu.compute_features(xyz, nn, nn_ptr, 1, "literal", f64=False)
+    s = cfg["search"]
+    if s[0] == "knn":
+        idx, _ = cpu.knn_search(xyz, xyz, s[1])                      # KD-tree build + query, all host threads
+        nn_ptr = (np.arange(xyz.shape[0] + 1) * s[1]).astype(np.uint32)   # README glue (README.md:135-141)
+        nn = idx.reshape(-1)
+    else:
+        idx, _ = cpu.radius_search(xyz, xyz, s[1], s[2])
+        nn_ptr = np.r_[0, (idx >= 0).sum(axis=1).cumsum()].astype(np.uint32)   # README.md:157-163
+        nn = idx[idx >= 0].astype(np.uint32)
+    f = cfg["feat"]
+    if f[0] == "features":
+        return cpu.compute_features(xyz, nn, nn_ptr, 1, "literal", f64=False)
+    if f[0] == "multiscale":
+        return cpu.compute_features_multiscale(xyz, nn, nn_ptr, f[1], "literal", f64=False)
+    return cpu.compute_features_optimal(xyz, nn, nn_ptr, f[1], f[2], f[3], "literal", f64=False)
+
+
+def sample_text(cfg, n_s):
+    return "%d-point sample of the %d-point %s cloud at equal density, same search and feature parameters, spatial index build included" % (
+        n_s, cfg["points"], cfg["cloud"])
 
 
 def run_reference(args, rank, real_stdout):
@@ -154,21 +225,20 @@ def run_reference(args, rank, real_stdout):
         return
     from oracle import cpu
     cpu.build()
-    n_s = min(args.cpu_sample, args.points)
-    xyz = sample_cloud(args.points, n_s)
+    cfg = args.cfg
+    n_s = cfg["cpu_sample"]
+    xyz = make_cloud(load_synth(), cfg, n_s, 0, cfg["points"])
     for _ in range(args.warmup):
-        cpu_step(cpu, xyz, args.knn)
+        cpu_step(cpu, cfg, xyz)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_step(cpu, xyz, args.knn)
+        cpu_step(cpu, cfg, xyz)
     dt = time.perf_counter() - t0
     value = n_s * args.steps / dt
-    sample = "%d-point sub-cube of the %d-point uniform cloud at equal density (same k=%d), KD-tree build included" % (n_s, args.points, args.knn)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "uniform [0,200)^3 float32 cloud, knn_search(k=%d) -> CSR -> compute_features (11 features)" % args.knn,
-                                            "points": args.points, "knn": args.knn, "sample_points": n_s},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.hardware_threads(), "kind": "port", "sample": sample},
+            "data": "synthetic", "config": {"workload": cfg["workload"], "points": cfg["points"], "sample_points": n_s},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.hardware_threads(), "kind": "port", "sample": sample_text(cfg, n_s)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(real_stdout, line)
 
@@ -189,8 +259,27 @@ def emit(real_stdout, line):
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
+def alg_bytes(cfg, rows, nnz):
+    """Algorithmic bytes per launch (SURVEY.md 8d): search 24 + 8k per row (CSR radius: 24 + 4 + 4 per neighbour kept);
+    features 48 + 16 k; multiscale 4k + 4 + 12k + 44 S; optimal 4k + 4 + 12k + 48."""
+    s, f = cfg["search"], cfg["feat"]
+    out = {}
+    if s[0] == "knn":
+        out["knn_search"] = (24 + 8 * s[1]) * rows
+    else:
+        out["radius_search"] = 28 * rows + 4 * nnz
+    if f[0] == "features":
+        out["features"] = 48 * rows + 16 * nnz
+    elif f[0] == "multiscale":
+        out["multiscale"] = (4 + 44 * len(f[1])) * rows + 16 * nnz
+    else:
+        out["optimal"] = 52 * rows + 16 * nnz
+    return out
+
+
 def _main(real_stdout):
     args = parse()
+    cfg = args.cfg
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,31 +308,50 @@ def _main(real_stdout):
         dist.init_process_group("nccl", device_id=dev)
     b200.set_eig_order("literal")
 
-    n, k = args.points, args.knn
+    n = cfg["points"]
+    search, feat = cfg["search"], cfg["feat"]
+    kk = search[1] if search[0] == "knn" else search[2]           # row capacity
     weak = args.scaling == "weak"
-    xyz = synth.uniform_cloud(n, seed=rank if weak else 0)         # strong: the same cloud on every rank (replicated)
-    lo, hi = (0, n) if weak else shard.shard_range(n, rank, world)
+    xyz = make_cloud(synth, cfg, n, seed=rank if weak else 0)       # strong: the same cloud on every rank (replicated)
     n_total = n * world if weak else n
     t = torch.from_numpy(xyz).to(dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # rows per CSR block: uint32 offsets hold 2^32-1 neighbours -> shard-local CSR blocks beyond that
+    block_rows = max(1, min(n, (0xFFFFFFFF // kk) // 1024 * 1024))
 
     debug = bool(os.environ.get("PGEOF_BENCH_DEBUG"))
     host_log = []
+
+    def features_of(cloud, nn, nn_ptr):
+        if feat[0] == "features":
+            return pgeof.compute_features(cloud, nn, nn_ptr)
+        if feat[0] == "multiscale":
+            return pgeof.compute_features_multiscale(cloud, nn, nn_ptr, feat[1])
+        return pgeof.compute_features_optimal(cloud, nn, nn_ptr, feat[1], feat[2], feat[3])
 
     def step():
         h0 = time.perf_counter()
         if world == 1 or weak:
             q = t
         else:                                                      # this rank's slab of the replicated cloud (no collective)
-            q = t[shard.spatial_shard(t, rank, world)]
-        idx, d2 = pgeof.knn_search(t, q, k)
-        h1 = time.perf_counter()
-        nn_ptr = (torch.arange(q.shape[0] + 1, device=dev, dtype=torch.int64) * k).to(torch.uint32)
-        h2 = time.perf_counter()
-        feats = pgeof.compute_features(t, idx.view(-1), nn_ptr)
+            q = shard.slab_queries(t, rank, world)[1]
+        outs, nnz = [], 0
+        for lo in range(0, q.shape[0], block_rows):                 # one block unless the CSR would overflow uint32 offsets
+            qb = q if block_rows >= q.shape[0] else q[lo:lo + block_rows]
+            if search[0] == "knn":
+                idx, d2 = pgeof.knn_search(t, qb, search[1])
+                nn = idx.view(-1)
+                nn_ptr = (torch.arange(qb.shape[0] + 1, device=dev, dtype=torch.int64) * search[1]).to(torch.uint32)
+                keep = (idx, d2)
+            else:
+                nn, nn_ptr = b200.radius_search_csr(t, qb, search[1], search[2])
+                keep = (nn, nn_ptr)
+            nnz += int(nn.shape[0])
+            f = features_of(t, nn, nn_ptr)
+            outs.append(keep + (f,))
         if debug:
-            host_log.append((1e3 * (h1 - h0), 1e3 * (h2 - h1), 1e3 * (time.perf_counter() - h2)))
-        return idx, d2, feats
+            host_log.append(1e3 * (time.perf_counter() - h0))
+        return outs, nnz, q.shape[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -273,14 +381,12 @@ def _main(real_stdout):
     barrier()
     t_wall1 = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_wall1)
-    launches = b200.launch_count() + 2 * args.steps               # + torch arange / cast per step (not ours, listed for honesty)
     own_launches = b200.launch_count()
     b200.profile_enable(False)
     step_ms = [s.elapsed_time(e) for s, e in ev]
     if debug and rank == 0:
         for i, ms in enumerate(step_ms):
-            h = host_log[len(host_log) - len(step_ms) + i]
-            print("step %d dev %.2f ms | host knn %.2f glue %.2f feat %.2f" % (i, ms, h[0], h[1], h[2]), file=sys.stderr)
+            print("step %d dev %.2f ms | host %.2f ms" % (i, ms, host_log[len(host_log) - len(step_ms) + i]), file=sys.stderr)
     dev_ms = sum(step_ms)
     tm = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -288,45 +394,61 @@ def _main(real_stdout):
     dev_ms_max = float(tm.item())
     value = n_total * args.steps / (dev_ms_max * 1e-3)
     kernels = {}
-    for name in ("knn_search", "features", "grid_build"):
+    for name in ("knn_search", "radius_search", "features", "multiscale", "optimal", "grid_build", "row_order"):
         ms, cnt = b200.profile_read(name)
-        kernels[name] = {"ms_per_launch": ms / max(cnt, 1), "launches": int(cnt)}
+        if cnt:
+            kernels[name] = {"ms_per_step": ms / args.steps, "launches_per_step": cnt / args.steps}
     # ---- roofline of the dominant kernel (algorithmic bytes of SURVEY.md 8d) --------------------
     peak, peak_src = peaks()
-    rows = int(out[0].shape[0]) if out is not None else hi - lo
-    alg = {"knn_search": (24 + 8 * k) * rows, "features": (48 + 16 * k) * rows}
-    dom = max(("knn_search", "features"), key=lambda nme: kernels[nme]["ms_per_launch"])
-    ach = alg[dom] / (kernels[dom]["ms_per_launch"] * 1e-3) / 1e9
-    # dram__bytes_read + dram__bytes_write per row from the latest `ncu --set full` capture (profiles/r1c_summary.md)
-    traffic_per_row = {"knn_search": 571.5, "features": 680.4}
+    _, nnz, rows_dev = out
+    alg = alg_bytes(cfg, rows_dev, nnz)
+    dom = max(alg, key=lambda nme: kernels.get(nme, {"ms_per_step": 0.0})["ms_per_step"])
+    dom_ms = kernels.get(dom, {"ms_per_step": float("nan")})["ms_per_step"]
+    ach = alg[dom] / (dom_ms * 1e-3) / 1e9
+    traffic, traffic_src = tracked_traffic()
+    per_row = traffic.get(cfg.get("traffic_key", args.config), {}).get(dom)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic_per_row[dom] * rows, "traffic_source": "profiles/r1c_summary.md (ncu --set full, 10 M rows, scaled by rows)",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                "note": "knn tile kernel is FP32/ALU-issue bound (622 candidate evaluations + a 985-comparator sorting network per query), not HBM bound; the gather-bound feature kernel is the one to read against the HBM roofline (all_kernels.features); see DESIGN.md",
-                "all_kernels": {nme: {"ms": kernels[nme]["ms_per_launch"],
-                                      "achieved_gbs": (alg[nme] / (kernels[nme]["ms_per_launch"] * 1e-3) / 1e9) if nme in alg and kernels[nme]["ms_per_launch"] > 0 else None}
+                "traffic": per_row * rows_dev if per_row else None, "traffic_source": traffic_src if per_row else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms_per_step": dom_ms,
+                "note": "search kernels are FP32/ALU-issue bound (distance evaluation + selection), not HBM bound; the gather-bound feature kernels are the ones to read against the HBM roofline (all_kernels); see DESIGN.md",
+                "all_kernels": {nme: {"ms": kernels[nme]["ms_per_step"],
+                                      "achieved_gbs": (alg[nme] / (kernels[nme]["ms_per_step"] * 1e-3) / 1e9) if nme in alg and kernels[nme]["ms_per_step"] > 0 else None}
                                 for nme in kernels}}
-
-    rows_dev = rows
     del out
-    rows = hi - lo
 
     # ---- end to end through the drop-in module with host buffers --------------------------------
     e2e = None
     if not args.no_e2e:
         e2e_steps = args.e2e_steps or args.steps
         hx = torch.from_numpy(xyz).pin_memory().numpy()             # pinned host input
-        hq = hx if (lo, hi) == (0, n) else hx[lo:hi]
+        if world == 1 or weak:
+            hq = hx
+        else:                                                       # the same spatial slab as the device leg
+            rows_t = shard.slab_queries(t, rank, world)[0]
+            hq = torch.from_numpy(xyz[rows_t.cpu().numpy()]).pin_memory().numpy()
+        rows = hq.shape[0]
+        e2e_block = max(1, min(rows, block_rows, int(os.environ.get("PGEOF_BENCH_E2E_BLOCK", "16000000"))))
 
         def host_step():
-            knn, _d2 = pgeof.knn_search(hx, hq, k)                  # numpy in -> numpy out (H2D + D2H inside)
-            nn_ptr = np.arange(0, (hi - lo + 1) * k, k, dtype=np.uint32)   # README glue (README.md:135-141) in one numpy pass
-            nn = knn.reshape(-1)                                    # zero-copy: knn is already uint32
-            f = pgeof.compute_features(hx, nn, nn_ptr)
-            return float(f[0, 0])                                   # read the result on the host
+            last, nnz_h = 0.0, 0
+            for lo in range(0, rows, e2e_block):
+                qb = hq if e2e_block >= rows else hq[lo:lo + e2e_block]
+                if search[0] == "knn":
+                    knn, _d2 = pgeof.knn_search(hx, qb, search[1])          # numpy in -> numpy out (H2D + D2H inside)
+                    nn_ptr = np.arange(0, (qb.shape[0] + 1) * search[1], search[1], dtype=np.uint32)   # README glue (README.md:135-141) in one numpy pass
+                    nn = knn.reshape(-1)                                    # zero-copy: knn is already uint32
+                else:
+                    ridx, _d2 = pgeof.radius_search(hx, qb, search[1], search[2])
+                    nn_ptr = np.r_[0, (ridx >= 0).sum(axis=1).cumsum()].astype(np.uint32)              # README.md:157-163
+                    nn = ridx[ridx >= 0].astype(np.uint32)
+                nnz_h += nn.shape[0]
+                f = features_of(hx, nn, nn_ptr)
+                last = float(f.reshape(-1)[0])                              # read the result on the host
+            return last, nnz_h
 
+        nnz_h = 0
         for _ in range(2):
-            host_step()
+            _, nnz_h = host_step()
         barrier()
         t0 = time.perf_counter()
         e2e_ms = []
@@ -340,39 +462,40 @@ def _main(real_stdout):
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dt = float(tm.item())
-        h2d = n * 12 + (0 if (lo, hi) == (0, n) else rows * 12) + n * 12 + rows * k * 4 + (rows + 1) * 4
-        d2h = rows * k * 8 + rows * 44
+        n_blocks = (rows + e2e_block - 1) // e2e_block
+        out_floats = {"features": 11, "multiscale": 11 * (len(feat[1]) if feat[0] == "multiscale" else 1), "optimal": 12}[feat[0]]
+        h2d = n_blocks * (n * 12 + n * 12) + (0 if hq is hx else rows * 12) + nnz_h * 4 + (rows + n_blocks) * 4
+        d2h = rows * kk * 8 + rows * out_floats * 4
         e2e = {"value": n_total * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * dt / e2e_steps, "steps": e2e_steps,
                "step_ms_min_median_max": [min(e2e_ms), statistics.median(e2e_ms), max(e2e_ms)],
-               "path": "pgeof.knn_search(numpy) -> reshape/arange glue -> pgeof.compute_features(numpy); pinned host input, pinned pooled outputs"}
+               "path": "pgeof search (numpy) -> README CSR glue in numpy -> pgeof features (numpy); pinned host input, pinned pooled outputs; %d query block(s) per step" % n_blocks}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import cpu
         cpu.build()
-        n_s = min(args.cpu_sample, n)
-        cx = sample_cloud(n, n_s)
-        cpu_step(cpu, cx, k)
+        n_s = cfg["cpu_sample"]
+        cx = make_cloud(synth, cfg, n_s, 0, n)
+        cpu_step(cpu, cfg, cx)
         reps, t0 = 0, time.perf_counter()
         while reps < 3 or time.perf_counter() - t0 < 10.0:
-            cpu_step(cpu, cx, k)
+            cpu_step(cpu, cfg, cx)
             reps += 1
             if time.perf_counter() - t0 > 30.0:
                 break
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": n_s * reps / dt, "unit": UNIT, "cores": cpu.hardware_threads(), "kind": "port",
-                        "sample": "%d-point sub-cube at equal density, %d repetitions, KD-tree build + kNN(k=%d) + CSR glue + compute_features" % (n_s, reps, k)}
+                        "sample": sample_text(cfg, n_s) + "; %d repetitions" % reps}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "uniform [0,200)^3 float32 cloud (seed 0), knn_search(k=%d) -> CSR view -> compute_features (11 features); grid build included in every step" % k,
-                           "points": n_total, "knn": k, "rows_per_rank": rows_dev,
-                           "parallelism": "query-sharded x%d (z slabs of ~n/N points from sample quantiles, computed inside the step), cloud and grid replicated, no data-path collective; e2e shards by contiguous row range" % world,
-                           "l2": "512 MiB buffer zeroed between timed iterations; per-step working set %.1f GB >> 126 MB L2" % ((rows * (k * 12 + 44) + n * 28) / 1e9),
+                "config": {"workload": cfg["workload"], "name": args.config, "points": n_total, "rows_per_rank": rows_dev, "neighbours_per_rank": nnz,
+                           "parallelism": "query-sharded x%d (z slabs of ~n/N points from a histogram of the replicated cloud, computed inside the step by the library), cloud replicated, grid clipped to the slab, no data-path collective; the e2e leg uses the same slabs" % world,
+                           "l2": "512 MiB buffer zeroed between timed iterations; per-step working set %.1f GB >> 126 MB L2" % ((nnz * 12 + rows_dev * 44 + n * 28) / 1e9),
                            "eig_order": "literal"},
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": int(own_launches), "gpu_launches_per_step": own_launches / args.steps,

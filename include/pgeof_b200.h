@@ -166,6 +166,25 @@ PGEOF_API int pgeof_compute_features_selected_f64_dev(const double* xyz, size_t 
  * (indices, sqr_dist) outputs are optional (NULL = not materialised for the caller). */
 PGEOF_API int pgeof_knn_features_dev(const float* xyz, size_t n, uint32_t knn, uint32_t k_min, int eig_order,
                                      uint32_t* indices, float* sqr_dist, float* features, void* stream);
+/* host flavour: 12 B per point up, 44 B per point down (+ 8 knn B per point if the lists are requested) */
+PGEOF_API int pgeof_knn_features(const float* xyz, size_t n, uint32_t knn, uint32_t k_min, int eig_order,
+                                 uint32_t* indices, float* sqr_dist, float* features);
+
+/* ---- spatial query shards for multi-GPU callers (extension) ---
+ * The reference has one Taskflow loop over all points (pgeof.hpp:91-109); across GPUs the independent rows are split
+ * into slabs along `axis`: slab `rank` of `world` holds ~n/world points, with edges from a 4096-bin histogram of the
+ * (replicated) cloud, identical on every rank without a collective.  _plan synchronises the stream once (the caller
+ * needs `count` to allocate); _fill writes the rows of the slab in input order and their coordinates. */
+typedef struct pgeof_slab_plan {
+    float lo, scale;            /* bin(v) = clamp(floor((v - lo) * scale), 0, 4095) */
+    uint32_t bin_lo, bin_hi;    /* the slab holds the points whose bin is in [bin_lo, bin_hi) */
+    uint64_t count;             /* rows of the slab */
+    int axis;
+} pgeof_slab_plan;
+PGEOF_API int pgeof_slab_plan_dev(const float* xyz, size_t n, int rank, int world, int axis, pgeof_slab_plan* plan,
+                                  void* stream);
+PGEOF_API int pgeof_slab_fill_dev(const float* xyz, size_t n, const pgeof_slab_plan* plan, int64_t* rows /* [count] */,
+                                  float* query /* [count, 3] */, void* stream);
 
 #ifdef __cplusplus
 }

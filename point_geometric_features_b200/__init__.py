@@ -43,6 +43,7 @@ from .pgeof_ext import (  # noqa: E402,F401
     radius_search_csr,
     reset_launch_count,
     set_eig_order,
+    slab_select,
     trim,
 )
 

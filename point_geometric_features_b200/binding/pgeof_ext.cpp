@@ -388,16 +388,31 @@ py::tuple radius_search_csr(const py::object& data, const py::object& query, flo
 py::object knn_features(const py::object& xyz, uint32_t knn, uint32_t k_min, bool return_neighbors)
 {
     ArrayView x = view_any(xyz, "xyz", kF32, 2);
-    if (!x.on_device) throw py::type_error("knn_features takes a CUDA tensor (the fused pipeline keeps every intermediate on the device)");
     if (knn > x.shape[0]) throw py::value_error("knn size is greater than the data point cloud size");
     Output feat = make_output(x, {x.shape[0], 11}, "float32", 4);
     Output idx, d2;
     if (return_neighbors) { idx = make_output(x, {x.shape[0], knn}, "uint32", 4); d2 = make_output(x, {x.shape[0], knn}, "float32", 4); }
     TorchStream ts(x);
     const int order = eig_order();
-    run_nogil([&] { return pgeof_knn_features_dev((const float*)x.ptr, x.shape[0], knn, k_min, order, (uint32_t*)idx.ptr, (float*)d2.ptr, (float*)feat.ptr, ts.stream); });
+    run_nogil([&] {
+        return x.on_device ? pgeof_knn_features_dev((const float*)x.ptr, x.shape[0], knn, k_min, order, (uint32_t*)idx.ptr, (float*)d2.ptr, (float*)feat.ptr, ts.stream)
+                           : pgeof_knn_features((const float*)x.ptr, x.shape[0], knn, k_min, order, (uint32_t*)idx.ptr, (float*)d2.ptr, (float*)feat.ptr);
+    });
     if (return_neighbors) return py::make_tuple(feat.obj, idx.obj, d2.obj);
     return feat.obj;
+}
+
+// rows (int64, input order) and coordinates of slab `rank` of `world` along `axis` of a replicated CUDA cloud
+py::tuple slab_select(const py::object& xyz, int rank, int world, int axis)
+{
+    ArrayView x = view_any(xyz, "xyz", kF32, 2);
+    if (!x.on_device) throw py::type_error("slab_select takes a CUDA tensor (host clouds: point_geometric_features_b200.shard.slab_queries)");
+    TorchStream ts(x);
+    pgeof_slab_plan plan;
+    run_nogil([&] { return pgeof_slab_plan_dev((const float*)x.ptr, x.shape[0], rank, world, axis, &plan, ts.stream); });
+    Output rows = make_torch({(size_t)plan.count}, "int64", x.torch_device), q = make_torch({(size_t)plan.count, 3}, "float32", x.torch_device);
+    run_nogil([&] { return pgeof_slab_fill_dev((const float*)x.ptr, x.shape[0], &plan, (int64_t*)rows.ptr, (float*)q.ptr, ts.stream); });
+    return py::make_tuple(rows.obj, q.obj);
 }
 
 }  // namespace
@@ -433,6 +448,8 @@ PYBIND11_MODULE(pgeof_ext, m)
           "Radius search emitting CSR directly -> (nn, nn_ptr) uint32.");
     m.def("knn_features", &knn_features, "xyz"_a.noconvert(), "knn"_a, "k_min"_a = 1, "return_neighbors"_a = false,
           "knn_search(xyz, xyz, knn) + compute_features in one device-resident call.");
+    m.def("slab_select", &slab_select, "xyz"_a.noconvert(), "rank"_a, "world"_a, "axis"_a = 2,
+          "Rows (int64, input order) and coordinates of spatial query shard `rank` of `world` along `axis` -> (rows, query).");
     m.def("set_eig_order", [](const std::string& s) {
         if (s == "literal") g_eig_order = PGEOF_EIG_LITERAL;
         else if (s == "documented") g_eig_order = PGEOF_EIG_DOCUMENTED;

@@ -17,6 +17,19 @@ namespace pgeof {
 thread_local uint64_t g_launches = 0;
 static thread_local char g_error[512] = "";
 
+int sm_count()
+{
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+    if (!cached[dev]) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; }
+        cached[dev] = sms;
+    }
+    return cached[dev];
+}
+
 void set_error(const char* fmt, ...)
 {
     va_list ap;
@@ -56,20 +69,50 @@ KernelTimer::~KernelTimer()
 // ---------------------------------------------------------------------------
 // device scratch: caching arena (see DeviceBuffer in common.cuh)
 // ---------------------------------------------------------------------------
-struct ArenaBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t event; };
+struct ArenaBlock { void* ptr; size_t bytes; cudaStream_t stream; cudaEvent_t event; uint64_t seq; };
 struct DeviceArena {
     std::mutex m;
     std::multimap<size_t, ArenaBlock> free_blocks[64];
+    size_t cached_bytes[64] = {};
+    size_t budget[64] = {};          // cap on cached (idle) bytes per device, 0 = not initialised yet
+    uint64_t seq = 0;
     static size_t round(size_t b) { const size_t g = b < ((size_t)1 << 20) ? 512 : ((size_t)2 << 20); return (b + g - 1) / g * g; }
     void trim_locked(int dev)
     {
         for (auto& kv : free_blocks[dev]) { cudaFree(kv.second.ptr); if (kv.second.event) cudaEventDestroy(kv.second.event); }
         free_blocks[dev].clear();
+        cached_bytes[dev] = 0;
+    }
+    // Idle blocks are kept for reuse up to a budget: PGEOF_ARENA_MAX_MB, default a quarter of the device's memory.  Beyond it
+    // the least recently released blocks go back to the driver (cudaFree synchronises; steady-state callers never get here),
+    // so a co-resident allocator (torch) is not starved by scratch of calls long past.
+    size_t budget_of(int dev)
+    {
+        if (!budget[dev]) {
+            size_t b = 0;
+            if (const char* e = std::getenv("PGEOF_ARENA_MAX_MB")) b = (size_t)std::strtoull(e, nullptr, 10) << 20;
+            else {
+                size_t free_b = 0, total_b = 0;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) b = total_b / 4; else cudaGetLastError();
+            }
+            budget[dev] = std::max<size_t>(b, (size_t)64 << 20);
+        }
+        return budget[dev];
+    }
+    void enforce_budget_locked(int dev)
+    {
+        const size_t cap = budget_of(dev);
+        while (cached_bytes[dev] > cap && !free_blocks[dev].empty()) {
+            auto oldest = free_blocks[dev].begin();
+            for (auto it = free_blocks[dev].begin(); it != free_blocks[dev].end(); ++it) if (it->second.seq < oldest->second.seq) oldest = it;
+            cudaFree(oldest->second.ptr);
+            if (oldest->second.event) cudaEventDestroy(oldest->second.event);
+            cached_bytes[dev] -= oldest->second.bytes;
+            free_blocks[dev].erase(oldest);
+        }
     }
 };
 static DeviceArena& arena() { static DeviceArena* a = new DeviceArena(); return *a; }   // leaked on purpose (exit order)
-
-static int ensure_pool(int) { return PGEOF_OK; }
 
 int DeviceBuffer::alloc(size_t want_bytes, cudaStream_t s)
 {
@@ -85,6 +128,7 @@ int DeviceBuffer::alloc(size_t want_bytes, cudaStream_t s)
         if (it != fl.end() && it->first <= want + want / 4 + ((size_t)1 << 20)) {
             const ArenaBlock blk = it->second;
             fl.erase(it);
+            ar.cached_bytes[dev] -= blk.bytes;
             // stream-ordered reuse: work queued on another stream before the release must be over first
             if (blk.stream != s && blk.event && cudaStreamWaitEvent(s, blk.event, 0) != cudaSuccess) cudaGetLastError();
             ptr = blk.ptr; bytes = blk.bytes; event = blk.event; stream = s; device = dev;
@@ -119,7 +163,14 @@ void DeviceBuffer::release()
     DeviceArena& ar = arena();
     {
         std::lock_guard<std::mutex> lock(ar.m);
-        ar.free_blocks[device].emplace(bytes, ArenaBlock{ptr, bytes, recorded ? stream : nullptr, ev});
+        ar.free_blocks[device].emplace(bytes, ArenaBlock{ptr, bytes, recorded ? stream : nullptr, ev, ++ar.seq});
+        ar.cached_bytes[device] += bytes;
+        int cur = -1;
+        if (ar.cached_bytes[device] > ar.budget_of(device) && cudaGetDevice(&cur) == cudaSuccess) {
+            if (cur != device) cudaSetDevice(device);
+            ar.enforce_budget_locked(device);
+            if (cur != device) cudaSetDevice(cur);
+        }
     }
     ptr = nullptr; bytes = 0; event = nullptr;
 }
@@ -144,7 +195,6 @@ static int ensure_device(int* device_out)
     }
     int dev = 0;
     PGEOF_CUDA(cudaGetDevice(&dev));
-    PGEOF_TRY(ensure_pool(dev));
     if (device_out) *device_out = dev;
     return PGEOF_OK;
 }
@@ -176,7 +226,7 @@ struct DeviceGuard {
             set_error("expected a CUDA device pointer");
             return PGEOF_EINVAL;
         }
-        if (attr.device != dev) { prev = dev; PGEOF_CUDA(cudaSetDevice(attr.device)); PGEOF_TRY(ensure_pool(attr.device)); }
+        if (attr.device != dev) { prev = dev; PGEOF_CUDA(cudaSetDevice(attr.device)); }
         return PGEOF_OK;
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
@@ -320,13 +370,20 @@ int pgeof_trim(void)
         std::lock_guard<std::mutex> lock(pinned_pool().m);
         pinned_pool().trim_locked();
     }
-    int dev = 0;
-    if (ensure_device(&dev) != PGEOF_OK) return PGEOF_OK;
-    PGEOF_CUDA(cudaDeviceSynchronize());
-    {
+    int cur = 0, count = 0;
+    if (ensure_device(&cur) != PGEOF_OK) return PGEOF_OK;
+    PGEOF_CUDA(cudaGetDeviceCount(&count));
+    for (int dev = 0; dev < count && dev < 64; ++dev) {      // every device this process left scratch on
+        {
+            std::lock_guard<std::mutex> lock(arena().m);
+            if (arena().free_blocks[dev].empty()) continue;
+        }
+        PGEOF_CUDA(cudaSetDevice(dev));
+        PGEOF_CUDA(cudaDeviceSynchronize());
         std::lock_guard<std::mutex> lock(arena().m);
         arena().trim_locked(dev);
     }
+    PGEOF_CUDA(cudaSetDevice(cur));
     return PGEOF_OK;
 }
 
@@ -676,6 +733,55 @@ int pgeof_knn_features_dev(const float* xyz, size_t n, uint32_t knn, uint32_t k_
     iota_scale_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(ptr.as<uint32_t>(), n + 1, knn);
     PGEOF_LAUNCH_CHECK();
     return features_run(xyz, n, indices, n * (size_t)knn, ptr.as<uint32_t>(), n, k_min, eig_order, features, s);
+}
+
+int pgeof_knn_features(const float* xyz, size_t n, uint32_t knn, uint32_t k_min, int eig_order, uint32_t* indices, float* sqr_dist,
+                       float* features)
+{
+    PGEOF_REQUIRE(knn <= n, "knn size is greater than the data point cloud size");
+    PGEOF_REQUIRE(k_min >= 1, "k_min should be > 1");
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && features, "null pointer argument");
+    DeviceBuffer d_xyz, d_idx, d_d2, d_feat;
+    PGEOF_TRY(h2d(&d_xyz, xyz, n * 12, s));
+    PGEOF_TRY(d_feat.alloc(n * 11 * 4, s));
+    const size_t rows = n * (size_t)knn;
+    if (indices) PGEOF_TRY(d_idx.alloc(std::max<size_t>(rows, 1) * 4, s));
+    if (sqr_dist) PGEOF_TRY(d_d2.alloc(std::max<size_t>(rows, 1) * 4, s));
+    PGEOF_TRY(pgeof_knn_features_dev(d_xyz.as<float>(), n, knn, k_min, eig_order, indices ? d_idx.as<uint32_t>() : nullptr,
+                                     sqr_dist ? d_d2.as<float>() : nullptr, d_feat.as<float>(), s));
+    PGEOF_TRY(d2h(features, d_feat, n * 11 * 4, s));
+    if (indices) PGEOF_TRY(d2h(indices, d_idx, rows * 4, s));
+    if (sqr_dist) PGEOF_TRY(d2h(sqr_dist, d_d2, rows * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
+// ------------------------------- query shards ------------------------------
+int pgeof_slab_plan_dev(const float* xyz, size_t n, int rank, int world, int axis, pgeof_slab_plan* plan, void* stream)
+{
+    PGEOF_REQUIRE(plan, "null pointer argument");
+    PGEOF_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bad rank / world");
+    PGEOF_REQUIRE(axis >= 0 && axis < 3, "axis must be 0, 1 or 2");
+    plan->lo = 0.f; plan->scale = 0.f; plan->bin_lo = 0; plan->bin_hi = 0; plan->count = 0; plan->axis = axis;
+    if (n == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz, "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(xyz));
+    return slab_plan_run(xyz, n, rank, world, axis, plan, (cudaStream_t)stream);
+}
+
+int pgeof_slab_fill_dev(const float* xyz, size_t n, const pgeof_slab_plan* plan, int64_t* rows, float* query, void* stream)
+{
+    PGEOF_REQUIRE(plan, "null pointer argument");
+    if (n == 0 || plan->count == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && rows && query, "null pointer argument");
+    PGEOF_REQUIRE(plan->axis >= 0 && plan->axis < 3 && plan->bin_lo <= plan->bin_hi, "bad slab plan");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(xyz));
+    return slab_fill_run(xyz, n, plan, reinterpret_cast<long long*>(rows), query, (cudaStream_t)stream);
 }
 
 }  // extern "C"

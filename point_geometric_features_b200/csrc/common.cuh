@@ -147,6 +147,13 @@ int bbox_partials(const float* xyz, size_t n, DeviceBuffer* out, int* n_partials
 // exclusive scan of `n` uint32 counts in place; writes the grand total to data[n]
 int exclusive_scan_u32(uint32_t* data, size_t n, cudaStream_t stream);
 
+// spatial query shards (shard.cu)
+int slab_plan_run(const float* xyz, size_t n, int rank, int world, int axis, pgeof_slab_plan* out, cudaStream_t stream);
+int slab_fill_run(const float* xyz, size_t n, const pgeof_slab_plan* plan, long long* rows, float* query, cudaStream_t stream);
+
+// multiprocessors of the current device (cached per device; 148 on B200)
+int sm_count();
+
 // device error flag helpers (EINDEX etc.)
 int device_flag_check(const int* d_flag, cudaStream_t stream, const char* what);
 

@@ -16,7 +16,7 @@ namespace pgeof {
 
 namespace {
 
-constexpr int kBBoxBlocks = 592;   // 4 x 148 SMs
+constexpr int kBBoxBlocks = 592;   // partial bounding boxes per cloud (a fixed count, sized as 4 CTAs per SM of a B200)
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) bbox_kernel(const float* __restrict__ xyz, size_t n, float* __restrict__ partial)

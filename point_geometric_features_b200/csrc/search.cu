@@ -28,6 +28,8 @@
 //    the points within a halo of that box; every ball radius is checked against GridView::rmax_safe and
 //    the queries that exceed it are re-run on the full grid.
 //
+//  * search_big_kernel (k > 512): one CTA per query, keys in global scratch, block-wide bitonic sort.
+//
 //  * search_kernel (kNN with 64 < k <= 512, radius modes): one warp per query.  Per query:
 //    (1) seed a radius from the local density of the 3x3x3 cell block, (2) scan the cells that
 //    intersect the ball, keeping keys under the threshold in a per-warp shared-memory buffer,
@@ -811,6 +813,196 @@ __global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// any k: one CTA per query, keys in GLOBAL scratch (knn / max_knn beyond the 512 the register-resident select + sort of
+// search_kernel covers; the reference accepts any knn <= len(data), nn_search.hpp:37,92).  Same exactness argument
+// as the warp routine: the ball is grown until it holds k points, the 64-bit key threshold is bisected while more than
+// `cap` keys pass it, the survivors are sorted by a block-wide bitonic network over global memory.  Built for
+// completeness, not speed: every query costs O(cap log^2 cap) global-memory compare-exchanges.
+// ---------------------------------------------------------------------------------------
+constexpr int kBigThreads = 256;
+
+// keys <= tau of ball(q, R): returns the count (block uniform); the first `cap` are appended to buf when STORE
+template <bool STORE>
+__device__ __forceinline__ uint32_t cta_scan_ball(const GridView& g, float qx, float qy, float qz, float R, u64 tau,
+                                                  u64* __restrict__ buf, uint32_t cap, uint32_t* s_count)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) *s_count = 0;
+    __syncthreads();
+    const int cx0 = cell_coord(__fsub_rd(qx, R), g.lo[0], g.inv_hx, g.n[0]);
+    const int cx1 = cell_coord(__fadd_ru(qx, R), g.lo[0], g.inv_hx, g.n[0]);
+    const int cy0 = cell_coord(__fsub_rd(qy, R), g.lo[1], g.inv_h, g.n[1]);
+    const int cy1 = cell_coord(__fadd_ru(qy, R), g.lo[1], g.inv_h, g.n[1]);
+    const int cz0 = cell_coord(__fsub_rd(qz, R), g.lo[2], g.inv_h, g.n[2]);
+    const int cz1 = cell_coord(__fadd_ru(qz, R), g.lo[2], g.inv_h, g.n[2]);
+    const int cqy = cell_coord(qy, g.lo[1], g.inv_h, g.n[1]);
+    const int cqz = cell_coord(qz, g.lo[2], g.inv_h, g.n[2]);
+    const uint32_t nyr = (uint32_t)(cy1 - cy0 + 1);
+    const uint32_t nrows = nyr * (uint32_t)(cz1 - cz0 + 1);
+    const float R2u = __fmul_ru(R, R);
+    const unsigned lt = lanemask_lt();
+    for (uint32_t r = warp; r < nrows; r += kBigThreads / 32) {       // one (y, z) cell row per warp
+        const int cz = cz0 + (int)(r / nyr), cy = cy0 + (int)(r % nyr);
+        const float gy = axis_gap(qy, cy, cqy, g.lo[1], g.h, g.slack);
+        const float gz = axis_gap(qz, cz, cqz, g.lo[2], g.h, g.slack);
+        const float rem = __fsub_ru(__fsub_ru(R2u, __fmul_rd(gy, gy)), __fmul_rd(gz, gz));
+        if (!(rem >= 0.f)) continue;
+        const float xr = __fsqrt_ru(rem);
+        const int x0 = max(cx0, cell_coord(__fsub_rd(qx, xr), g.lo[0], g.inv_hx, g.n[0]));
+        const int x1 = min(cx1, cell_coord(__fadd_ru(qx, xr), g.lo[0], g.inv_hx, g.n[0]));
+        const uint32_t row = ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0];
+        const uint32_t s = __ldg(g.cell_start + row + x0), e = __ldg(g.cell_start + row + x1 + 1);
+        for (uint32_t base = s; base < e; base += 32) {
+            const uint32_t j = base + lane;
+            bool acc = false;
+            u64 key = 0;
+            if (j < e) {
+                const float4 p = __ldg(g.pts + j);
+                key = make_key(sqdist_f32(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
+                acc = key <= tau;
+            }
+            const unsigned m = __ballot_sync(kFull, acc);
+            if (m) {
+                uint32_t at = 0;
+                if (lane == 0) at = atomicAdd(s_count, (uint32_t)__popc(m));
+                at = __shfl_sync(kFull, at, 0);
+                if (STORE && acc) {
+                    const uint32_t pos = at + __popc(m & lt);
+                    if (pos < cap) buf[pos] = key;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t c = *s_count;
+    __syncthreads();
+    return c;
+}
+
+// ascending bitonic sort of buf[0, n), n a power of two, by the whole block
+__device__ __forceinline__ void cta_bitonic_sort(u64* __restrict__ buf, uint32_t n)
+{
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < n / 2; t += kBigThreads) {
+                const uint32_t lo = 2 * t - (t & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const u64 a = buf[lo], b = buf[hi];
+                if ((a > b) == asc) { buf[lo] = b; buf[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBigThreads) search_big_kernel(const GridView g, const SearchArgs a, u64* __restrict__ scratch, uint32_t cap)
+{
+    __shared__ uint32_t s_count;
+    u64* buf = scratch + (size_t)blockIdx.x * cap;
+    const uint32_t k = a.k;
+    for (uint32_t w = blockIdx.x; w < a.n_query; w += gridDim.x) {
+        const float4 q4 = __ldg(a.queries + w);
+        const float qx = q4.x, qy = q4.y, qz = q4.z;
+        const uint32_t row = __float_as_uint(q4.w);
+        uint32_t c = 0;          // keys <= tau, stored in buf (c <= cap when the loops end)
+        uint32_t need = k;
+        u64 tau = 0;
+        if (MODE == SEARCH_KNN) {
+            // ball seeded from the global density, grown until it holds k points; then the threshold is bisected while it overflows
+            float R = fmaxf(a.target, 1e-30f) + bbox_distance(g, qx, qy, qz);
+            u64 tau_lo = 0, tau_hi = 0;
+            bool have_hi = false;
+            float Rg = R;
+            tau = tau_from_radius(R);
+            for (int it = 0; it < 600; ++it) {
+                c = cta_scan_ball<true>(g, qx, qy, qz, Rg, tau, buf, cap, &s_count);
+                if (c < k) {
+                    tau_lo = tau;
+                    if (have_hi) tau = tau_lo + (tau_hi - tau_lo) / 2;
+                    else { R *= 1.35f; Rg = R; tau = tau_from_radius(R); }
+                } else if (c > cap) {
+                    tau_hi = tau; have_hi = true;
+                    tau = tau_lo + (tau_hi - tau_lo) / 2;                  // Rg stays: it covers every key <= tau_hi
+                } else break;
+            }
+        } else {
+            const float r2 = __fmul_rn(a.radius, a.radius);                   // nn_search.hpp:98
+            if (r2 > 0.f) {
+                tau = ((u64)__float_as_uint(r2) << 32) - 1;                   // d2 < r2, strict
+                const float Rg = __fmul_ru(__fsqrt_ru(r2), 1.0001f);
+                c = cta_scan_ball<true>(g, qx, qy, qz, Rg, tau, buf, cap, &s_count);
+                need = min(c, k);
+                if (c > cap) {                                                // more than cap (>= 2k) inside: keep between k and cap of the nearest
+                    u64 tau_lo = 0, tau_hi = tau;
+                    for (int it = 0; it < 600; ++it) {
+                        tau = tau_lo + (tau_hi - tau_lo) / 2;
+                        c = cta_scan_ball<true>(g, qx, qy, qz, Rg, tau, buf, cap, &s_count);
+                        if (c < k) tau_lo = tau; else if (c > cap) tau_hi = tau; else break;
+                    }
+                }
+            } else need = 0;
+        }
+        // sort what was kept (padded to a power of two)
+        uint32_t n = 1;
+        while (n < c) n <<= 1;
+        for (uint32_t t = c + threadIdx.x; t < n; t += kBigThreads) buf[t] = kKeyMax;
+        __syncthreads();
+        cta_bitonic_sort(buf, n);
+        if (MODE == SEARCH_KNN) {
+            uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)row * k;
+            float* d2 = a.sqr_dist + (size_t)row * k;
+            for (uint32_t e = threadIdx.x; e < k; e += kBigThreads) { idx[e] = key_idx(buf[e]); d2[e] = key_d2(buf[e]); }
+        } else if (MODE == SEARCH_RADIUS) {
+            int32_t* idx = reinterpret_cast<int32_t*>(a.indices) + (size_t)row * k;
+            float* d2 = a.sqr_dist + (size_t)row * k;
+            for (uint32_t e = threadIdx.x; e < k; e += kBigThreads) {      // pad: -1 / 0 (nn_search.hpp:104,108)
+                const bool hit = e < need;
+                idx[e] = hit ? (int32_t)key_idx(buf[e]) : -1;
+                d2[e] = hit ? key_d2(buf[e]) : 0.f;
+            }
+        } else {   // SEARCH_RADIUS_CSR
+            const uint32_t base = a.nn_ptr[row];
+            uint32_t* nn = reinterpret_cast<uint32_t*>(a.indices);
+            for (uint32_t e = threadIdx.x; e < need; e += kBigThreads) {
+                nn[(size_t)base + e] = key_idx(buf[e]);
+                if (a.sqr_dist) a.sqr_dist[(size_t)base + e] = key_d2(buf[e]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int MODE>
+int launch_big(const GridView& g, SearchArgs a, size_t n_data, cudaStream_t stream)
+{
+    // capacity: a power of two >= 2k (room for the ball to overshoot), at least 2048
+    uint64_t cap = 2048;
+    while (cap < 2ull * a.k) cap <<= 1;
+    if (cap > 0x80000000ull) { set_error("knn / max_knn = %u is too large", a.k); return PGEOF_EINVAL; }
+    const int sms = sm_count();
+    const uint64_t budget = 1ull << 30;                                     // bytes of key scratch
+    const uint64_t blocks = std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)a.n_query, (uint64_t)sms * 8, budget / (cap * sizeof(u64))}));
+    DeviceBuffer scratch;
+    PGEOF_TRY(scratch.alloc((size_t)(blocks * cap * sizeof(u64)), stream));
+    if (MODE == SEARCH_KNN) {
+        // radius of a ball that holds ~1.2 k points at the mean density of the indexed box
+        double vol = 1;
+        int dims = 0;
+        for (int d = 0; d < 3; ++d) { const double e = (double)g.n[d] * (d == 0 ? g.hx : g.h); if (e > 0) { vol *= e; ++dims; } }
+        const double per = vol / (double)std::max<size_t>(n_data, 1);
+        a.target = (float)std::cbrt(1.2 * a.k * per / 4.18879);
+    }
+    {
+        KernelTimer timer(MODE == SEARCH_KNN ? "knn_search" : "radius_search", stream);
+        search_big_kernel<MODE><<<(unsigned)blocks, kBigThreads, 0, stream>>>(g, a, scratch.as<u64>(), (uint32_t)cap);
+    }
+    PGEOF_LAUNCH_CHECK();
+    return PGEOF_OK;
+}
+
 template <int NSORT, int MODE>
 int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
@@ -838,8 +1030,8 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     {
         KernelTimer timer(MODE == SEARCH_KNN ? "knn_search" : "radius_search", stream);
         kern<<<blocks, Cfg::WARPS * 32, smem, stream>>>(g, a);
-        if (MODE == SEARCH_KNN) knn_slow_kernel<NOUT><<<148 * 4, kWarps * 32, 0, stream>>>(g, a);
-        else search_list_kernel<NOUT, SEARCH_RADIUS><<<148 * 4, kWarps * 32, (size_t)kWarps * SearchCfg<NOUT, SEARCH_RADIUS>::CAP * sizeof(u64), stream>>>(g, a);
+        if (MODE == SEARCH_KNN) knn_slow_kernel<NOUT><<<sm_count() * 4, kWarps * 32, 0, stream>>>(g, a);
+        else search_list_kernel<NOUT, SEARCH_RADIUS><<<sm_count() * 4, kWarps * 32, (size_t)kWarps * SearchCfg<NOUT, SEARCH_RADIUS>::CAP * sizeof(u64), stream>>>(g, a);
     }
     PGEOF_LAUNCH_CHECK();
     PGEOF_LAUNCH_CHECK();
@@ -854,15 +1046,14 @@ float env_float(const char* name, float dflt);
 inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : 96; }
 
 template <int MODE>
-int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, cudaStream_t stream)
+int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, size_t n_data, cudaStream_t stream)
 {
     if (k <= 32) return launch_search<32, MODE>(g, a, stream);
     if (k <= 64) return launch_search<64, MODE>(g, a, stream);
     if (k <= 128) return launch_search<128, MODE>(g, a, stream);
     if (k <= 256) return launch_search<256, MODE>(g, a, stream);
     if (k <= 512) return launch_search<512, MODE>(g, a, stream);
-    set_error("knn / max_knn = %u exceeds the supported maximum of 512 neighbours per query", k);
-    return PGEOF_EINVAL;
+    return launch_big<MODE>(g, a, n_data, stream);   // any knn <= len(data), as the reference (nn_search.hpp:37,92)
 }
 
 __global__ void iota_scale_u32(uint32_t* out, size_t n, uint32_t k)
@@ -887,7 +1078,9 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     Grid grid;
     float target = 0.f;
     const bool tile = (mode == SEARCH_KNN ? env_float("PGEOF_KNN_TILE", 1.f) != 0.f : mode == SEARCH_RADIUS && env_float("PGEOF_RADIUS_TILE", 1.f) != 0.f) && k <= 64;
-    if (mode != SEARCH_KNN && (!(radius >= 0.f) || !std::isfinite(radius))) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
+    // the reference only ever uses r * r (nn_search.hpp:98): a negative radius searches the ball of |r|
+    if (mode != SEARCH_KNN && !std::isfinite(radius)) { set_error("search_radius must be finite"); return PGEOF_EINVAL; }
+    radius = std::fabs(radius);
     float occ = 0.f, edge = 0.f;
     int xf = 1;
     if (mode == SEARCH_KNN) {
@@ -970,8 +1163,8 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
                 SearchArgs b = a;
                 b.slow_list = a.unsafe_list;
                 b.slow_count = a.unsafe_count;
-                if (k <= 32) knn_slow_kernel<32><<<148 * 4, kWarps * 32, 0, stream>>>(full.view, b);
-                else knn_slow_kernel<64><<<148 * 4, kWarps * 32, 0, stream>>>(full.view, b);
+                if (k <= 32) knn_slow_kernel<32><<<sm_count() * 4, kWarps * 32, 0, stream>>>(full.view, b);
+                else knn_slow_kernel<64><<<sm_count() * 4, kWarps * 32, 0, stream>>>(full.view, b);
                 PGEOF_LAUNCH_CHECK();
             }
         }
@@ -991,10 +1184,10 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         return st;
     }
     switch (mode) {
-        case SEARCH_KNN: return dispatch_search<SEARCH_KNN>(k, grid.view, a, stream);
-        case SEARCH_RADIUS: return dispatch_search<SEARCH_RADIUS>(k, grid.view, a, stream);
+        case SEARCH_KNN: return dispatch_search<SEARCH_KNN>(k, grid.view, a, n_data, stream);
+        case SEARCH_RADIUS: return dispatch_search<SEARCH_RADIUS>(k, grid.view, a, n_data, stream);
         case SEARCH_RADIUS_COUNT: return launch_search<32, SEARCH_RADIUS_COUNT>(grid.view, a, stream);
-        case SEARCH_RADIUS_CSR: return dispatch_search<SEARCH_RADIUS_CSR>(k, grid.view, a, stream);
+        case SEARCH_RADIUS_CSR: return dispatch_search<SEARCH_RADIUS_CSR>(k, grid.view, a, n_data, stream);
     }
     return PGEOF_EINVAL;
 }

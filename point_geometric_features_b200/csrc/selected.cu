@@ -229,7 +229,9 @@ int selected_run(const T* xyz, const float* xyz_f32, size_t n, T radius, uint32_
                  int eig_order, T* out, cudaStream_t stream)
 {
     if (n == 0 || n_ids == 0) return PGEOF_OK;
-    if (!(radius >= T(0)) || !std::isfinite((double)radius)) { set_error("search_radius must be finite and >= 0"); return PGEOF_EINVAL; }
+    // the reference only ever uses r * r (pgeof.hpp:336): a negative radius searches the ball of |r|
+    if (!std::isfinite((double)radius)) { set_error("search_radius must be finite"); return PGEOF_EINVAL; }
+    radius = radius < T(0) ? -radius : radius;
     if (eig_order != PGEOF_EIG_LITERAL && eig_order != PGEOF_EIG_DOCUMENTED) { set_error("bad eig_order %d", eig_order); return PGEOF_EINVAL; }
     Grid grid;
     const float edge = (float)radius > 0.f ? (float)radius : 1.f;

@@ -11,8 +11,8 @@ Which rows a rank owns is a free choice.  ``shard_range`` (contiguous row ranges
 cloud in random order, leaves every rank with queries spread thinly over the WHOLE volume: the kNN tile
 kernel shares one candidate region between 32 neighbouring queries, so its cost per query grows as the
 queries thin out (measured: 5 M of 10 M random rows cost 7.1 ms against 7.7 ms for all 10 M).
-``spatial_shard`` therefore gives rank r a SLAB along one axis holding ~n/world points (quantiles of a
-sorted sample, computed identically on every rank from the replicated cloud, no collective), which keeps the
+``slab_queries`` / ``spatial_shard`` therefore give rank r a SLAB along one axis holding ~n/world points (edges from
+a 4096-bin histogram of the replicated cloud, computed identically on every rank, no collective), which keeps the
 query density of a single-GPU run; ``gather_rows_indexed`` puts such row blocks back in input order.
 
 ``gather_rows`` / ``gather_rows_indexed`` (optional, off the timed path) reassemble per-rank row blocks
@@ -41,25 +41,42 @@ def local_knn_csr(n_local, k, torch, device):
     return (torch.arange(n_local + 1, device=device, dtype=torch.int64) * k).to(torch.uint32)
 
 
-def spatial_shard(xyz, rank, world, axis=2, sample=65536):
-    """Row ids (ascending, int64) of rank ``rank``'s slab along ``axis``.  The slabs partition the rows; their edges
-    are the k/world quantiles of a strided sample of ``sample`` coordinates (sorted on the device: a handful of small
-    kernels), so every slab holds n/world points up to the sampling error (~1 % at world = 8).  ``xyz`` is the
-    replicated (n, 3) cloud as a torch tensor (any device); every rank derives the same edges, so no exchange is needed."""
+SLAB_BINS = 4096
+
+
+def slab_queries(xyz, rank, world, axis=2):
+    """``(rows, query)`` of rank ``rank``'s slab along ``axis``: row ids (ascending int64) and their coordinates.
+
+    The slabs partition the rows.  Their edges come from a 4096-bin histogram of the replicated cloud (slab r = the bins
+    whose exclusive prefix count lies in [r n / world, (r + 1) n / world)), so every slab holds n/world points up to the
+    mass of one bin and every rank derives the same edges with no exchange.  CUDA tensors go through the library
+    (``pgeof_slab_plan_dev`` / ``pgeof_slab_fill_dev``: three streaming passes and one host synchronisation); host tensors
+    use the torch restatement below, bin for bin the same arithmetic (it is what the gloo tests exercise)."""
     import torch
 
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank/world")
     n = xyz.shape[0]
-    if world == 1 or n == 0:
-        return torch.arange(n, device=xyz.device)
-    c = xyz[:, axis]
-    s = torch.sort(c[:: max(1, n // sample)]).values
-    m = s.shape[0]
-    lo_ok = c >= s[(rank * m) // world] if rank > 0 else None
-    hi_ok = c < s[((rank + 1) * m) // world] if rank + 1 < world else None
-    mask = lo_ok if hi_ok is None else (hi_ok if lo_ok is None else lo_ok & hi_ok)
-    return torch.nonzero(mask).squeeze(1)
+    if xyz.is_cuda:
+        from . import slab_select
+        return slab_select(xyz, rank, world, axis)
+    if n == 0:
+        return torch.arange(0), xyz
+    c = xyz[:, axis].to(torch.float32)
+    lo, hi = c.min(), c.max()
+    ext = hi - lo
+    scale = torch.tensor(float(SLAB_BINS), dtype=torch.float32) / ext if float(ext) > 0 else torch.tensor(0.0)
+    bins = ((c - lo) * scale).floor().clamp(0, SLAB_BINS - 1).to(torch.int64)
+    cum = torch.cat([torch.zeros(1, dtype=torch.int64), torch.bincount(bins, minlength=SLAB_BINS).cumsum(0)])
+    target = torch.tensor([(rank * n) // world, ((rank + 1) * n) // world])
+    b_lo, b_hi = (int(v) for v in torch.searchsorted(cum, target, right=False))     # smallest b with cum[b] >= target
+    rows = torch.nonzero((bins >= b_lo) & (bins < b_hi)).squeeze(1)
+    return rows, xyz[rows]
+
+
+def spatial_shard(xyz, rank, world, axis=2):
+    """Row ids (ascending, int64) of rank ``rank``'s slab along ``axis`` (see ``slab_queries``)."""
+    return slab_queries(xyz, rank, world, axis)[0]
 
 
 def knn_features_shard(xyz, k, rank, world, k_min=1, spatial=True):
@@ -76,8 +93,7 @@ def knn_features_shard(xyz, k, rank, world, k_min=1, spatial=True):
     if world == 1:
         rows, query = torch.arange(xyz.shape[0], device=xyz.device), xyz
     elif spatial:
-        rows = spatial_shard(xyz, rank, world)
-        query = xyz[rows]
+        rows, query = slab_queries(xyz, rank, world)
     else:
         lo, hi = shard_range(xyz.shape[0], rank, world)
         rows, query = torch.arange(lo, hi, device=xyz.device), xyz[lo:hi]

@@ -159,3 +159,32 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d
     assert d["impl"] == "reference" and d["unit"] == "points/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("config", ["C3", "C4", "C5"])
+def test_bench_reference_arm_runs_every_config(config):
+    """The other BASELINE.json configurations behind --config: same one-line contract, bounded CPU sample."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", config, "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "5000"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip())
+    assert d["impl"] == "reference" and d["value"] > 0 and d["config"]["sample_points"] == 5000
+
+
+def test_reference_arm_maps_no_product_library():
+    """The CPU arm must not load the CUDA library or the binding: run it under an import hook that fails on them."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, runpy\n"
+            "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-sample', '3000']\n"
+            "runpy.run_path(%r, run_name='__main__')\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libpgeof_b200' not in maps and 'pgeof_ext' not in maps, 'product library mapped by the reference arm'\n"
+            "assert 'point_geometric_features_b200' not in sys.modules\n") % os.path.join(root, "bench.py")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]

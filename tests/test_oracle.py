@@ -156,8 +156,8 @@ def test_golden_fixture_still_reproduced():
         # through 1/(s0 + 1e-3) in the literal order
         rnn, rptr = radius_csr(cpu.radius_search(xyz, xyz, 0.15, 12)[0])
         ev = row_eigvals(xyz, rnn, rptr)
-        compare_features(s64, g["selected_f64_" + order], ev, order, "selected f64", ids)
-        stats = compare_features(s32, g["selected_f32_" + order], ev, order, "selected f32", ids)
+        compare_features(s64, g["selected_f64_" + order], ev, order, "selected f64", ids, max_weak=0.05, max_degenerate=0.2, max_ill=0.2)
+        stats = compare_features(s32, g["selected_f32_" + order], ev, order, "selected f32", ids, max_weak=0.05, max_degenerate=0.2, max_ill=0.2)
         assert stats["degenerate_rows"] < 0.2 * len(xyz)
     # README glue for a radius result (README.md:157-163)
     nn_r, ptr_r = radius_csr(ridx)
