@@ -103,10 +103,12 @@ PGEOF_API int pgeof_radius_search_dev(const float* data, size_t n_data, const fl
                                       float search_radius, uint32_t max_knn, int32_t* indices, float* sqr_dist,
                                       void* stream);
 
-/* Extension: radius search emitting CSR directly (count + scan + fill).
- * nn_ptr (n_query+1) uint32 is written; *nnz receives the total.  Call once with
- * nn == NULL to size nn (nn_ptr and *nnz are produced), then again with nn to fill.
- * The _dev flavour synchronises `stream` to read *nnz back. */
+/* Extension: radius search emitting CSR directly -- what the README glue
+ * (README.md:157-163) builds from the padded result.  nn_ptr (n_query+1) uint32 is written; *nnz
+ * receives the total.  Call once with nn == NULL to size nn (nn_ptr and *nnz are produced), then
+ * again with the same arguments and nn to fill it: the pair runs ONE search (the padded table of
+ * the first call stays parked in library scratch, per host thread, until the second call, the next
+ * first call or pgeof_trim).  The first call synchronises `stream` to read *nnz back. */
 PGEOF_API int pgeof_radius_search_csr(const float* data, size_t n_data, const float* query, size_t n_query,
                                       float search_radius, uint32_t max_knn, uint32_t* nn_ptr, uint32_t* nn,
                                       uint64_t* nnz);
@@ -114,7 +116,18 @@ PGEOF_API int pgeof_radius_search_csr_dev(const float* data, size_t n_data, cons
                                           float search_radius, uint32_t max_knn, uint32_t* nn_ptr, uint32_t* nn,
                                           uint64_t* nnz, void* stream);
 
+/* Extension: kNN emitting CSR directly -- nn = the (n_query, knn) table of
+ * nanoflann_knn_search (nn_search.hpp:31-67) flattened, nn_ptr[i] = i * knn with ptr_bits = 32
+ * (uint32_t*, the reference's dtype) or 64 (uint64_t*: the README's "known limitation" of
+ * 2^32-1 neighbours per CSR, README.md:187-195, does not apply).  No squared distances. */
+PGEOF_API int pgeof_knn_search_csr(const float* data, size_t n_data, const float* query, size_t n_query,
+                                   uint32_t knn, uint32_t* nn, void* nn_ptr, int ptr_bits);
+PGEOF_API int pgeof_knn_search_csr_dev(const float* data, size_t n_data, const float* query, size_t n_query,
+                                       uint32_t knn, uint32_t* nn, void* nn_ptr, int ptr_bits, void* stream);
+
 /* ---- neighbourhood-PCA features (replaces include/pca.hpp + pgeof.hpp) --- */
+/* Every CSR feature function also exists with uint64 row offsets (_p64: extension; the reference
+ * binds uint32 only, pgeof.hpp:78-79, which caps one CSR at 2^32-1 neighbours). */
 /* compute_geometric_features<float,11>, pgeof.hpp:75-117 / pgeof_ext.cpp:34.
  * out (n_rows,11); rows shorter than k_min stay 0.  k_min < 1 -> PGEOF_EINVAL. */
 PGEOF_API int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
@@ -160,6 +173,28 @@ PGEOF_API int pgeof_compute_features_selected_f64(const double* xyz, size_t n, d
 PGEOF_API int pgeof_compute_features_selected_f64_dev(const double* xyz, size_t n, double search_radius,
                                                       uint32_t max_knn, const int32_t* feature_ids,
                                                       size_t n_features, int eig_order, double* out, void* stream);
+
+/* uint64 row offsets (extension, see above): same semantics as the uint32 functions */
+PGEOF_API int pgeof_compute_features_p64(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
+                                         const uint64_t* nn_ptr, size_t n_rows, uint32_t k_min, int eig_order,
+                                         float* out);
+PGEOF_API int pgeof_compute_features_p64_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
+                                             const uint64_t* nn_ptr, size_t n_rows, uint32_t k_min, int eig_order,
+                                             float* out, void* stream);
+PGEOF_API int pgeof_compute_features_multiscale_p64(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
+                                                    const uint64_t* nn_ptr, size_t n_rows, const uint32_t* k_scales,
+                                                    size_t n_scales, int eig_order, float* out);
+PGEOF_API int pgeof_compute_features_multiscale_p64_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
+                                                        const uint64_t* nn_ptr, size_t n_rows,
+                                                        const uint32_t* k_scales, size_t n_scales, int eig_order,
+                                                        float* out, void* stream);
+PGEOF_API int pgeof_compute_features_optimal_p64(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
+                                                 const uint64_t* nn_ptr, size_t n_rows, uint32_t k_min,
+                                                 uint32_t k_step, uint32_t k_min_search, int eig_order, float* out);
+PGEOF_API int pgeof_compute_features_optimal_p64_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
+                                                     const uint64_t* nn_ptr, size_t n_rows, uint32_t k_min,
+                                                     uint32_t k_step, uint32_t k_min_search, int eig_order,
+                                                     float* out, void* stream);
 
 /* ---- fused pipeline (extension) --------------------------- */
 /* knn_search(xyz, xyz, knn) -> CSR view -> compute_features in one call; the

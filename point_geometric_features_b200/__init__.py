@@ -36,6 +36,7 @@ from .pgeof_ext import (  # noqa: E402,F401
     device_count,
     get_eig_order,
     knn_features,
+    knn_search_csr,
     launch_count,
     profile_enable,
     profile_read,

@@ -76,7 +76,7 @@ bool is_torch_tensor(const py::object& o)
 
 // typestr of __cuda_array_interface__ / numpy for the dtype a parameter requires
 struct DType { const char* name; char kind; int itemsize; };
-constexpr DType kF32{"float32", 'f', 4}, kF64{"float64", 'f', 8}, kU32{"uint32", 'u', 4};
+constexpr DType kF32{"float32", 'f', 4}, kF64{"float64", 'f', 8}, kU32{"uint32", 'u', 4}, kU64{"uint64", 'u', 8}, kI64{"int64", 'i', 8};
 
 [[noreturn]] void type_error(const char* arg, const DType& want, const std::string& got)
 {
@@ -260,11 +260,29 @@ py::tuple radius_search(const py::object& data, const py::object& query, float s
 struct Csr {
     ArrayView xyz, nn, ptr;
     size_t n_rows;
+    bool p64;     // nn_ptr holds 64-bit offsets (extension; the reference binds uint32 only, pgeof.hpp:78-79)
 };
+
+// 8-byte integer offsets: numpy uint64 / int64, torch uint64 / int64 (torch's usual index dtype)
+int wide_offsets(const py::object& o)
+{
+    std::string name;
+    if (is_numpy(o)) {
+        const py::dtype dt = py::reinterpret_borrow<py::array>(o).dtype();
+        if (dt.itemsize() == 8 && dt.kind() == 'u') return 1;
+        if (dt.itemsize() == 8 && dt.kind() == 'i') return 2;
+        return 0;
+    }
+    if (py::hasattr(o, "dtype")) name = py::str(o.attr("dtype")).cast<std::string>();
+    if (name == "torch.uint64") return 1;
+    if (name == "torch.int64") return 2;
+    return 0;
+}
 
 Csr view_csr(const py::object& xyz, const py::object& nn, const py::object& nn_ptr)
 {
-    Csr c{view_any(xyz, "xyz", kF32, 2), view_any(nn, "nn", kU32, 1), view_any(nn_ptr, "nn_ptr", kU32, 1), 0};
+    const int wide = wide_offsets(nn_ptr);
+    Csr c{view_any(xyz, "xyz", kF32, 2), view_any(nn, "nn", kU32, 1), view_any(nn_ptr, "nn_ptr", wide == 1 ? kU64 : (wide == 2 ? kI64 : kU32), 1), 0, wide != 0};
     same_space({&c.xyz, &c.nn, &c.ptr});
     if (c.ptr.shape[0] == 0) throw py::value_error("nn_ptr must hold at least one offset");   // reference underflows (pgeof.hpp:83)
     c.n_rows = c.ptr.shape[0] - 1;
@@ -279,6 +297,10 @@ py::object compute_features(const py::object& xyz, const py::object& nn, const p
     TorchStream ts(c.xyz);
     const int order = eig_order();
     run_nogil([&] {
+        if (c.p64)
+            return c.xyz.on_device
+                       ? pgeof_compute_features_p64_dev((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint64_t*)c.ptr.ptr, c.n_rows, (uint32_t)k_min, order, (float*)out.ptr, ts.stream)
+                       : pgeof_compute_features_p64((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint64_t*)c.ptr.ptr, c.n_rows, (uint32_t)k_min, order, (float*)out.ptr);
         return c.xyz.on_device
                    ? pgeof_compute_features_dev((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint32_t*)c.ptr.ptr, c.n_rows, (uint32_t)k_min, order, (float*)out.ptr, ts.stream)
                    : pgeof_compute_features((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint32_t*)c.ptr.ptr, c.n_rows, (uint32_t)k_min, order, (float*)out.ptr);
@@ -298,6 +320,10 @@ py::object compute_features_multiscale(const py::object& xyz, const py::object& 
     TorchStream ts(c.xyz);
     const int order = eig_order();
     run_nogil([&] {
+        if (c.p64)
+            return c.xyz.on_device
+                       ? pgeof_compute_features_multiscale_p64_dev((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint64_t*)c.ptr.ptr, c.n_rows, scales.data(), scales.size(), order, (float*)out.ptr, ts.stream)
+                       : pgeof_compute_features_multiscale_p64((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint64_t*)c.ptr.ptr, c.n_rows, scales.data(), scales.size(), order, (float*)out.ptr);
         return c.xyz.on_device
                    ? pgeof_compute_features_multiscale_dev((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint32_t*)c.ptr.ptr, c.n_rows, scales.data(), scales.size(), order, (float*)out.ptr, ts.stream)
                    : pgeof_compute_features_multiscale((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint32_t*)c.ptr.ptr, c.n_rows, scales.data(), scales.size(), order, (float*)out.ptr);
@@ -316,6 +342,10 @@ py::object compute_features_optimal(const py::object& xyz, const py::object& nn,
     TorchStream ts(c.xyz);
     const int order = eig_order();
     run_nogil([&] {
+        if (c.p64)
+            return c.xyz.on_device
+                       ? pgeof_compute_features_optimal_p64_dev((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint64_t*)c.ptr.ptr, c.n_rows, k_min, k_step, k_min_search, order, (float*)out.ptr, ts.stream)
+                       : pgeof_compute_features_optimal_p64((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint64_t*)c.ptr.ptr, c.n_rows, k_min, k_step, k_min_search, order, (float*)out.ptr);
         return c.xyz.on_device
                    ? pgeof_compute_features_optimal_dev((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint32_t*)c.ptr.ptr, c.n_rows, k_min, k_step, k_min_search, order, (float*)out.ptr, ts.stream)
                    : pgeof_compute_features_optimal((const float*)c.xyz.ptr, c.xyz.shape[0], (const uint32_t*)c.nn.ptr, c.nn.shape[0], (const uint32_t*)c.ptr.ptr, c.n_rows, k_min, k_step, k_min_search, order, (float*)out.ptr);
@@ -385,6 +415,25 @@ py::tuple radius_search_csr(const py::object& data, const py::object& query, flo
     return py::make_tuple(nn.obj, ptr.obj);
 }
 
+// kNN emitting CSR: (nn uint32 (n * knn), nn_ptr uint32 -- or int64 / uint64 when the CSR holds more than 2^32-1 neighbours or on request)
+py::tuple knn_search_csr(const py::object& data, const py::object& query, uint32_t knn, bool wide_offsets_requested)
+{
+    ArrayView d = view_any(data, "data", kF32, 2), q = view_any(query, "query", kF32, 2);
+    same_space({&d, &q});
+    if (knn > d.shape[0]) throw py::value_error("knn size is greater than the data point cloud size");
+    const bool wide = wide_offsets_requested || (uint64_t)q.shape[0] * knn > 0xffffffffull;
+    Output nn = make_output(q, {q.shape[0] * (size_t)knn}, "uint32", 4);
+    // torch indexes with int64 and has little uint64 support: wide offsets are int64 on tensors, uint64 on numpy arrays
+    Output ptr = wide ? make_output(q, {q.shape[0] + 1}, q.on_device ? "int64" : "uint64", 8) : make_output(q, {q.shape[0] + 1}, "uint32", 4);
+    TorchStream ts(d);
+    const float* qp = data.is(query) ? (const float*)d.ptr : (const float*)q.ptr;
+    run_nogil([&] {
+        return d.on_device ? pgeof_knn_search_csr_dev((const float*)d.ptr, d.shape[0], qp, q.shape[0], knn, (uint32_t*)nn.ptr, ptr.ptr, wide ? 64 : 32, ts.stream)
+                           : pgeof_knn_search_csr((const float*)d.ptr, d.shape[0], qp, q.shape[0], knn, (uint32_t*)nn.ptr, ptr.ptr, wide ? 64 : 32);
+    });
+    return py::make_tuple(nn.obj, ptr.obj);
+}
+
 py::object knn_features(const py::object& xyz, uint32_t knn, uint32_t k_min, bool return_neighbors)
 {
     ArrayView x = view_any(xyz, "xyz", kF32, 2);
@@ -446,6 +495,8 @@ PYBIND11_MODULE(pgeof_ext, m)
     // extensions
     m.def("radius_search_csr", &radius_search_csr, "data"_a.noconvert(), "query"_a.noconvert(), "search_radius"_a, "max_knn"_a,
           "Radius search emitting CSR directly -> (nn, nn_ptr) uint32.");
+    m.def("knn_search_csr", &knn_search_csr, "data"_a.noconvert(), "query"_a.noconvert(), "knn"_a, "wide_offsets"_a = false,
+          "kNN emitting CSR directly -> (nn uint32, nn_ptr uint32; 64-bit offsets beyond 2^32-1 neighbours or with wide_offsets=True).");
     m.def("knn_features", &knn_features, "xyz"_a.noconvert(), "knn"_a, "k_min"_a = 1, "return_neighbors"_a = false,
           "knn_search(xyz, xyz, knn) + compute_features in one device-resident call.");
     m.def("slab_select", &slab_select, "xyz"_a.noconvert(), "rank"_a, "world"_a, "axis"_a = 2,

@@ -331,6 +331,26 @@ __global__ void iota_scale_kernel(uint32_t* out, size_t n, uint32_t k)
 
 using namespace pgeof;
 
+// parked state of a radius_search_csr call pair (see pgeof_radius_search_csr_dev / pgeof_radius_search_csr)
+struct PendingCsr {
+    const float* data = nullptr; const float* query = nullptr;
+    size_t n_data = 0, n_query = 0;
+    float radius = 0.f; uint32_t max_knn = 0;
+    const uint32_t* nn_ptr = nullptr;
+    int device = -1;
+    DeviceBuffer idx;
+    void clear() { idx.release(); data = query = nullptr; nn_ptr = nullptr; n_data = n_query = 0; }
+};
+static thread_local PendingCsr g_pending_csr;
+struct PendingCsrHost {
+    const float* data = nullptr; const float* query = nullptr; const uint32_t* nn_ptr = nullptr;
+    size_t n_data = 0, n_query = 0;
+    float radius = 0.f; uint32_t max_knn = 0;
+    DeviceBuffer d_data, d_query, d_ptr;
+    void clear() { d_data.release(); d_query.release(); d_ptr.release(); data = query = nullptr; nn_ptr = nullptr; }
+};
+static thread_local PendingCsrHost g_pending_csr_host;
+
 #define PGEOF_REQUIRE(cond, ...)                                  \
     do {                                                          \
         if (!(cond)) { set_error(__VA_ARGS__); return PGEOF_EINVAL; } \
@@ -366,6 +386,8 @@ void pgeof_reset_launch_count(void) { g_launches = 0; }
 
 int pgeof_trim(void)
 {
+    g_pending_csr.clear();            // parked scratch of a radius_search_csr pair (this thread's)
+    g_pending_csr_host.clear();
     {
         std::lock_guard<std::mutex> lock(pinned_pool().m);
         pinned_pool().trim_locked();
@@ -459,6 +481,64 @@ int pgeof_knn_search(const float* data, size_t n_data, const float* query, size_
     return PGEOF_OK;
 }
 
+// kNN straight into CSR (extension): nn = the (n_query, knn) index table flattened, nn_ptr = row * knn in
+// uint32 or -- beyond 2^32-1 neighbours, the README's "known limitation" -- uint64.  The squared distances are not
+// returned (2 GB less to write out / copy back at 10 M x 50).
+__global__ void iota_scale64_kernel(unsigned long long* out, size_t n, uint32_t k)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (unsigned long long)i * k;
+}
+
+int pgeof_knn_search_csr_dev(const float* data, size_t n_data, const float* query, size_t n_query, uint32_t knn, uint32_t* nn,
+                             void* nn_ptr, int ptr_bits, void* stream)
+{
+    PGEOF_REQUIRE(knn <= n_data, "knn size is greater than the data point cloud size");
+    PGEOF_REQUIRE(ptr_bits == 32 || ptr_bits == 64, "ptr_bits must be 32 or 64");
+    PGEOF_REQUIRE(nn_ptr, "null pointer argument");
+    PGEOF_REQUIRE(ptr_bits == 64 || (uint64_t)n_query * knn <= 0xffffffffull, "n_query * knn exceeds the uint32 CSR limit: ask for 64-bit offsets or shard the queries");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(nn_ptr));
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned blocks = (unsigned)((n_query + 1 + 255) / 256);
+    if (ptr_bits == 32) iota_scale_kernel<<<blocks, 256, 0, s>>>((uint32_t*)nn_ptr, n_query + 1, knn);
+    else iota_scale64_kernel<<<blocks, 256, 0, s>>>((unsigned long long*)nn_ptr, n_query + 1, knn);
+    PGEOF_LAUNCH_CHECK();
+    if (n_query == 0 || knn == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(data && query && nn, "null pointer argument");
+    DeviceBuffer d2;
+    PGEOF_TRY(d2.alloc(n_query * (size_t)knn * 4, s));
+    return search_run(SEARCH_KNN, data, n_data, query, n_query, knn, 0.f, nn, d2.as<float>(), nullptr, s);
+}
+
+int pgeof_knn_search_csr(const float* data, size_t n_data, const float* query, size_t n_query, uint32_t knn, uint32_t* nn, void* nn_ptr,
+                         int ptr_bits)
+{
+    PGEOF_REQUIRE(knn <= n_data, "knn size is greater than the data point cloud size");
+    PGEOF_REQUIRE(ptr_bits == 32 || ptr_bits == 64, "ptr_bits must be 32 or 64");
+    PGEOF_REQUIRE(nn_ptr, "null pointer argument");
+    PGEOF_REQUIRE(ptr_bits == 64 || (uint64_t)n_query * knn <= 0xffffffffull, "n_query * knn exceeds the uint32 CSR limit: ask for 64-bit offsets or shard the queries");
+    // the offsets are arithmetic: written on the host
+    if (ptr_bits == 32) for (size_t i = 0; i <= n_query; ++i) ((uint32_t*)nn_ptr)[i] = (uint32_t)(i * knn);
+    else for (size_t i = 0; i <= n_query; ++i) ((uint64_t*)nn_ptr)[i] = (uint64_t)i * knn;
+    cudaStream_t s;
+    PGEOF_TRY(host_stream(&s));
+    if (n_query == 0 || knn == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(data && query && nn, "null pointer argument");
+    DeviceBuffer d_data, d_query, d_idx, d_d2;
+    PGEOF_TRY(h2d(&d_data, data, n_data * 12, s));
+    const bool self = (query == data && n_query == n_data);
+    if (!self) PGEOF_TRY(h2d(&d_query, query, n_query * 12, s));
+    const size_t out_elems = n_query * (size_t)knn;
+    PGEOF_TRY(d_idx.alloc(out_elems * 4, s));
+    PGEOF_TRY(d_d2.alloc(out_elems * 4, s));
+    PGEOF_TRY(search_run(SEARCH_KNN, d_data.as<float>(), n_data, self ? d_data.as<float>() : d_query.as<float>(), n_query, knn, 0.f,
+                         d_idx.ptr, d_d2.as<float>(), nullptr, s));
+    PGEOF_TRY(d2h(nn, d_idx, out_elems * 4, s));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    return PGEOF_OK;
+}
+
 int pgeof_radius_search_dev(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
                             uint32_t max_knn, int32_t* indices, float* sqr_dist, void* stream)
 {
@@ -493,6 +573,33 @@ int pgeof_radius_search(const float* data, size_t n_data, const float* query, si
     return PGEOF_OK;
 }
 
+// Radius search straight into CSR.  Called twice (the caller allocates nn once the total is known): with nn == NULL it
+// writes the row offsets and returns the total, with nn it writes the neighbours.  ONE search serves both calls: the first
+// runs the padded search into library scratch, counts and scans; the scratch stays parked (per host thread) and the second
+// call only compacts it.  If the second call does not match the parked search (other arguments, other thread) it searches
+// again -- same result, one search slower.
+
+__global__ void padded_row_count_kernel(const int32_t* __restrict__ idx, size_t n_rows, uint32_t max_knn, uint32_t* __restrict__ counts)
+{
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t c = 0;
+    for (uint32_t j = lane; j < max_knn; j += 32) c += __ldg(idx + row * max_knn + j) >= 0 ? 1u : 0u;   // hits are a prefix of the row
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[row] = c;
+}
+
+__global__ void padded_compact_kernel(const int32_t* __restrict__ idx, size_t n_rows, uint32_t max_knn, const uint32_t* __restrict__ nn_ptr,
+                                      uint32_t* __restrict__ nn)
+{
+    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t b = __ldg(nn_ptr + row), len = __ldg(nn_ptr + row + 1) - b;
+    for (uint32_t j = lane; j < len; j += 32) nn[(size_t)b + j] = (uint32_t)__ldg(idx + row * max_knn + j);
+}
+
 int pgeof_radius_search_csr_dev(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
                                 uint32_t max_knn, uint32_t* nn_ptr, uint32_t* nn, uint64_t* nnz, void* stream)
 {
@@ -503,20 +610,52 @@ int pgeof_radius_search_csr_dev(const float* data, size_t n_data, const float* q
     DeviceGuard guard;
     PGEOF_TRY(guard.enter(nn_ptr));
     cudaStream_t s = (cudaStream_t)stream;
-    if (!nn) {   // pass 1: count + scan
+    PendingCsr& pend = g_pending_csr;
+    int dev = -1;
+    PGEOF_CUDA(cudaGetDevice(&dev));
+    // scratch of the single-search path: the padded (n_query, max_knn) table of indices and distances (8 B per slot)
+    const bool single = std::getenv("PGEOF_RADIUS_CSR_TWO_PASS") == nullptr && (uint64_t)n_query * max_knn * 8ull <= (16ull << 30);
+    if (!nn) {   // call 1: offsets + total
+        pend.clear();
         PGEOF_CUDA(cudaMemsetAsync(nn_ptr, 0, (n_query + 1) * sizeof(uint32_t), s));
-        if (n_query && max_knn)
-            PGEOF_TRY(search_run(SEARCH_RADIUS_COUNT, data, n_data, query, n_query, max_knn, search_radius, nullptr, nullptr, nn_ptr, s));
+        if (n_query && max_knn) {
+            if (single) {
+                DeviceBuffer d2;
+                PGEOF_TRY(pend.idx.alloc(n_query * (size_t)max_knn * 4, s));
+                PGEOF_TRY(d2.alloc(n_query * (size_t)max_knn * 4, s));
+                PGEOF_TRY(search_run(SEARCH_RADIUS, data, n_data, query, n_query, max_knn, search_radius, pend.idx.ptr, d2.as<float>(), nullptr, s));
+                padded_row_count_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, s>>>(pend.idx.as<int32_t>(), n_query, max_knn, nn_ptr);
+                PGEOF_LAUNCH_CHECK();
+                pend.data = data; pend.query = query; pend.n_data = n_data; pend.n_query = n_query; pend.radius = search_radius;
+                pend.max_knn = max_knn; pend.nn_ptr = nn_ptr; pend.device = dev;
+            } else {
+                PGEOF_TRY(search_run(SEARCH_RADIUS_COUNT, data, n_data, query, n_query, max_knn, search_radius, nullptr, nullptr, nn_ptr, s));
+            }
+        }
         PGEOF_TRY(exclusive_scan_u32(nn_ptr, n_query, s));
         uint32_t total = 0;
         PGEOF_CUDA(cudaMemcpyAsync(&total, nn_ptr + n_query, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         PGEOF_CUDA(cudaStreamSynchronize(s));
         *nnz = total;
+        if (total == 0) pend.clear();
         return PGEOF_OK;
     }
-    if (n_query == 0 || max_knn == 0) return PGEOF_OK;
+    if (n_query == 0 || max_knn == 0) { pend.clear(); return PGEOF_OK; }
+    const bool parked = pend.idx.ptr && pend.data == data && pend.query == query && pend.n_data == n_data && pend.n_query == n_query &&
+                        pend.radius == search_radius && pend.max_knn == max_knn && pend.nn_ptr == nn_ptr && pend.device == dev &&
+                        pend.idx.stream == s;
+    if (parked) {   // call 2 of the pair: compact the parked table
+        padded_compact_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, s>>>(pend.idx.as<int32_t>(), n_query, max_knn, nn_ptr, nn);
+        PGEOF_LAUNCH_CHECK();
+        pend.clear();
+        return PGEOF_OK;
+    }
+    pend.clear();
     return search_run(SEARCH_RADIUS_CSR, data, n_data, query, n_query, max_knn, search_radius, nn, nullptr, nn_ptr, s);
 }
+
+// host flavour: the device copies of the cloud / queries / offsets stay parked between the two calls as well, so the pair
+// uploads the cloud once and searches once
 
 int pgeof_radius_search_csr(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
                             uint32_t max_knn, uint32_t* nn_ptr, uint32_t* nn, uint64_t* nnz)
@@ -525,82 +664,133 @@ int pgeof_radius_search_csr(const float* data, size_t n_data, const float* query
     PGEOF_REQUIRE(nn_ptr && nnz, "null pointer argument");
     cudaStream_t s;
     PGEOF_TRY(host_stream(&s));
-    DeviceBuffer d_data, d_query, d_ptr, d_nn;
-    PGEOF_TRY(h2d(&d_data, data, n_data * 12, s));
+    PendingCsrHost& pend = g_pending_csr_host;
     const bool self = (query == data && n_query == n_data);
-    if (!self) PGEOF_TRY(h2d(&d_query, query, n_query * 12, s));
-    const float* dq = self ? d_data.as<float>() : d_query.as<float>();
-    PGEOF_TRY(d_ptr.alloc((n_query + 1) * 4, s));
+    const bool parked = nn && pend.d_ptr.ptr && pend.data == data && pend.query == query && pend.n_data == n_data && pend.n_query == n_query &&
+                        pend.radius == search_radius && pend.max_knn == max_knn && pend.nn_ptr == nn_ptr && pend.d_ptr.stream == s;
+    if (!parked) {
+        pend.clear();
+        g_pending_csr.clear();
+        PGEOF_TRY(h2d(&pend.d_data, data, n_data * 12, s));
+        if (!self) PGEOF_TRY(h2d(&pend.d_query, query, n_query * 12, s));
+        PGEOF_TRY(pend.d_ptr.alloc((n_query + 1) * 4, s));
+    }
+    const float* dq = self ? pend.d_data.as<float>() : pend.d_query.as<float>();
     if (!nn) {
-        PGEOF_TRY(pgeof_radius_search_csr_dev(d_data.as<float>(), n_data, dq, n_query, search_radius, max_knn, d_ptr.as<uint32_t>(), nullptr, nnz, s));
-        PGEOF_TRY(d2h(nn_ptr, d_ptr, (n_query + 1) * 4, s));
+        const int st = pgeof_radius_search_csr_dev(pend.d_data.as<float>(), n_data, dq, n_query, search_radius, max_knn, pend.d_ptr.as<uint32_t>(), nullptr, nnz, s);
+        if (st != PGEOF_OK) { pend.clear(); return st; }
+        PGEOF_TRY(d2h(nn_ptr, pend.d_ptr, (n_query + 1) * 4, s));
         PGEOF_CUDA(cudaStreamSynchronize(s));
+        pend.data = data; pend.query = query; pend.n_data = n_data; pend.n_query = n_query; pend.radius = search_radius; pend.max_knn = max_knn;
+        pend.nn_ptr = nn_ptr;
         return PGEOF_OK;
     }
-    PGEOF_CUDA(cudaMemcpyAsync(d_ptr.ptr, nn_ptr, (n_query + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (!parked) PGEOF_CUDA(cudaMemcpyAsync(pend.d_ptr.ptr, nn_ptr, (n_query + 1) * 4, cudaMemcpyHostToDevice, s));
     const size_t total = nn_ptr[n_query];
-    PGEOF_TRY(d_nn.alloc(total * 4, s));
-    PGEOF_TRY(pgeof_radius_search_csr_dev(d_data.as<float>(), n_data, dq, n_query, search_radius, max_knn, d_ptr.as<uint32_t>(), d_nn.as<uint32_t>(), nnz, s));
-    PGEOF_TRY(d2h(nn, d_nn, total * 4, s));
-    PGEOF_CUDA(cudaStreamSynchronize(s));
+    DeviceBuffer d_nn;
+    int st = d_nn.alloc(std::max<size_t>(total, 1) * 4, s);
+    if (st == PGEOF_OK) st = pgeof_radius_search_csr_dev(pend.d_data.as<float>(), n_data, dq, n_query, search_radius, max_knn, pend.d_ptr.as<uint32_t>(), d_nn.as<uint32_t>(), nnz, s);
+    if (st == PGEOF_OK) st = d2h(nn, d_nn, total * 4, s);
+    if (st == PGEOF_OK && cudaStreamSynchronize(s) != cudaSuccess) { cudaGetLastError(); set_error("stream synchronisation failed"); st = PGEOF_ECUDA; }
+    pend.clear();
+    g_pending_csr.clear();
+    if (st != PGEOF_OK) return st;
     *nnz = total;
     return PGEOF_OK;
 }
 
 // ------------------------------- features ----------------------------------
-int pgeof_compute_features_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
-                               size_t n_rows, uint32_t k_min, int eig_order, float* out, void* stream)
+// Every CSR feature function exists in four flavours: {host, device} buffers x {uint32 (reference dtype), uint64} row offsets.
+static int features_dev_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr ptr, size_t n_rows, uint32_t k_min,
+                             int eig_order, float* out, void* stream)
 {
     PGEOF_REQUIRE(k_min >= 1, "k_min should be > 1");                                   // pgeof.hpp:81
     if (n_rows == 0) return PGEOF_OK;
-    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    PGEOF_REQUIRE(xyz && (ptr.p32 || ptr.p64) && out && (nn || nnz == 0), "null pointer argument");
     DeviceGuard guard;
-    PGEOF_TRY(guard.enter(nn_ptr));
-    return features_run(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, k_min, eig_order, out, (cudaStream_t)stream);
+    PGEOF_TRY(guard.enter(ptr.p32 ? (const void*)ptr.p32 : (const void*)ptr.p64));
+    return features_run(xyz, n_xyz, nn, nnz, ptr, n_rows, k_min, eig_order, out, (cudaStream_t)stream);
+}
+
+static int multiscale_dev_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr ptr, size_t n_rows,
+                               const uint32_t* k_scales, size_t n_scales, int eig_order, float* out, void* stream)
+{
+    PGEOF_REQUIRE(n_scales == 0 || k_scales, "null pointer argument");
+    PGEOF_REQUIRE(check_scales(k_scales, n_scales), "k_scales should be > 1 and sorted in ascending order");   // pgeof.hpp:165-168
+    if (n_rows == 0 || n_scales == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && (ptr.p32 || ptr.p64) && out && (nn || nnz == 0), "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(ptr.p32 ? (const void*)ptr.p32 : (const void*)ptr.p64));
+    return features_multiscale_run(xyz, n_xyz, nn, nnz, ptr, n_rows, k_scales, n_scales, eig_order, out, (cudaStream_t)stream);
+}
+
+static int optimal_dev_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr ptr, size_t n_rows, uint32_t k_min,
+                            uint32_t k_step, uint32_t k_min_search, int eig_order, float* out, void* stream)
+{
+    PGEOF_REQUIRE(!(k_min < 1 && k_min_search < 1), "k_min and k_min_search should be > 1");   // pgeof.hpp:250 (sic)
+    PGEOF_REQUIRE(k_step >= 1, "k_step should be >= 1");                                      // reference: modulo by zero
+    if (n_rows == 0) return PGEOF_OK;
+    PGEOF_REQUIRE(xyz && (ptr.p32 || ptr.p64) && out && (nn || nnz == 0), "null pointer argument");
+    DeviceGuard guard;
+    PGEOF_TRY(guard.enter(ptr.p32 ? (const void*)ptr.p32 : (const void*)ptr.p64));
+    return features_optimal_run(xyz, n_xyz, nn, nnz, ptr, n_rows, k_min, k_step, k_min_search, eig_order, out, (cudaStream_t)stream);
+}
+
+int pgeof_compute_features_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                               size_t n_rows, uint32_t k_min, int eig_order, float* out, void* stream)
+{
+    return features_dev_core(xyz, n_xyz, nn, nnz, RowPtr(nn_ptr), n_rows, k_min, eig_order, out, stream);
+}
+int pgeof_compute_features_p64_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint64_t* nn_ptr,
+                                   size_t n_rows, uint32_t k_min, int eig_order, float* out, void* stream)
+{
+    return features_dev_core(xyz, n_xyz, nn, nnz, RowPtr(reinterpret_cast<const unsigned long long*>(nn_ptr)), n_rows, k_min, eig_order, out, stream);
 }
 
 int pgeof_compute_features_multiscale_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
                                           size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out,
                                           void* stream)
 {
-    PGEOF_REQUIRE(n_scales == 0 || k_scales, "null pointer argument");
-    PGEOF_REQUIRE(check_scales(k_scales, n_scales), "k_scales should be > 1 and sorted in ascending order");   // pgeof.hpp:165-168
-    if (n_rows == 0 || n_scales == 0) return PGEOF_OK;
-    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
-    DeviceGuard guard;
-    PGEOF_TRY(guard.enter(nn_ptr));
-    return features_multiscale_run(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, k_scales, n_scales, eig_order, out, (cudaStream_t)stream);
+    return multiscale_dev_core(xyz, n_xyz, nn, nnz, RowPtr(nn_ptr), n_rows, k_scales, n_scales, eig_order, out, stream);
+}
+int pgeof_compute_features_multiscale_p64_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint64_t* nn_ptr,
+                                              size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out,
+                                              void* stream)
+{
+    return multiscale_dev_core(xyz, n_xyz, nn, nnz, RowPtr(reinterpret_cast<const unsigned long long*>(nn_ptr)), n_rows, k_scales, n_scales, eig_order, out, stream);
 }
 
 int pgeof_compute_features_optimal_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
                                        size_t n_rows, uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order,
                                        float* out, void* stream)
 {
-    PGEOF_REQUIRE(!(k_min < 1 && k_min_search < 1), "k_min and k_min_search should be > 1");   // pgeof.hpp:250 (sic)
-    PGEOF_REQUIRE(k_step >= 1, "k_step should be >= 1");                                      // reference: modulo by zero
-    if (n_rows == 0) return PGEOF_OK;
-    PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
-    DeviceGuard guard;
-    PGEOF_TRY(guard.enter(nn_ptr));
-    return features_optimal_run(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, k_min, k_step, k_min_search, eig_order, out, (cudaStream_t)stream);
+    return optimal_dev_core(xyz, n_xyz, nn, nnz, RowPtr(nn_ptr), n_rows, k_min, k_step, k_min_search, eig_order, out, stream);
+}
+int pgeof_compute_features_optimal_p64_dev(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint64_t* nn_ptr,
+                                           size_t n_rows, uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order,
+                                           float* out, void* stream)
+{
+    return optimal_dev_core(xyz, n_xyz, nn, nnz, RowPtr(reinterpret_cast<const unsigned long long*>(nn_ptr)), n_rows, k_min, k_step, k_min_search, eig_order, out, stream);
 }
 
-// host flavours of the three CSR feature functions share the staging code
+// host flavours of the CSR feature functions share the staging code
 struct CsrOnDevice {
     DeviceBuffer xyz, nn, ptr, out;
-    int stage(const float* h_xyz, size_t n_xyz, const uint32_t* h_nn, size_t nnz, const uint32_t* h_ptr, size_t n_rows, size_t out_floats,
+    RowPtr dptr{(const uint32_t*)nullptr};
+    int stage(const float* h_xyz, size_t n_xyz, const uint32_t* h_nn, size_t nnz, const void* h_ptr, int ptr_bytes, size_t n_rows, size_t out_floats,
               cudaStream_t s)
     {
         PGEOF_TRY(h2d(&xyz, h_xyz, n_xyz * 12, s));
         PGEOF_TRY(h2d(&nn, h_nn, nnz * 4, s));
-        PGEOF_TRY(h2d(&ptr, h_ptr, (n_rows + 1) * 4, s));
+        PGEOF_TRY(h2d(&ptr, h_ptr, (n_rows + 1) * (size_t)ptr_bytes, s));
         PGEOF_TRY(out.alloc(out_floats * 4, s));
+        dptr = ptr_bytes == 8 ? RowPtr(ptr.as<unsigned long long>()) : RowPtr(ptr.as<uint32_t>());
         return PGEOF_OK;
     }
 };
 
-int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
-                           uint32_t k_min, int eig_order, float* out)
+static int features_host_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const void* nn_ptr, int ptr_bytes, size_t n_rows,
+                              uint32_t k_min, int eig_order, float* out)
 {
     PGEOF_REQUIRE(k_min >= 1, "k_min should be > 1");
     cudaStream_t s;
@@ -609,9 +799,9 @@ int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, s
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
     HostTrace trace("compute_features", s);
     CsrOnDevice d;
-    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * 11, s));
+    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_rows * 11, s));
     trace.mark("alloc+h2d");
-    PGEOF_TRY(features_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_min, eig_order, d.out.as<float>(), s));
+    PGEOF_TRY(features_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.dptr, n_rows, k_min, eig_order, d.out.as<float>(), s));
     trace.mark("features");
     PGEOF_TRY(d2h(out, d.out, n_rows * 11 * 4, s));
     PGEOF_CUDA(cudaStreamSynchronize(s));
@@ -619,8 +809,8 @@ int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, s
     return PGEOF_OK;
 }
 
-int pgeof_compute_features_multiscale(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
-                                      size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out)
+static int multiscale_host_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const void* nn_ptr, int ptr_bytes, size_t n_rows,
+                                const uint32_t* k_scales, size_t n_scales, int eig_order, float* out)
 {
     PGEOF_REQUIRE(n_scales == 0 || k_scales, "null pointer argument");
     PGEOF_REQUIRE(check_scales(k_scales, n_scales), "k_scales should be > 1 and sorted in ascending order");
@@ -629,16 +819,16 @@ int pgeof_compute_features_multiscale(const float* xyz, size_t n_xyz, const uint
     if (n_rows == 0 || n_scales == 0) return PGEOF_OK;
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
     CsrOnDevice d;
-    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * n_scales * 11, s));
-    PGEOF_TRY(features_multiscale_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_scales, n_scales,
+    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_rows * n_scales * 11, s));
+    PGEOF_TRY(features_multiscale_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.dptr, n_rows, k_scales, n_scales,
                                       eig_order, d.out.as<float>(), s));
     PGEOF_TRY(d2h(out, d.out, n_rows * n_scales * 11 * 4, s));
     PGEOF_CUDA(cudaStreamSynchronize(s));
     return PGEOF_OK;
 }
 
-int pgeof_compute_features_optimal(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
-                                   uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out)
+static int optimal_host_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const void* nn_ptr, int ptr_bytes, size_t n_rows,
+                             uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out)
 {
     PGEOF_REQUIRE(!(k_min < 1 && k_min_search < 1), "k_min and k_min_search should be > 1");
     PGEOF_REQUIRE(k_step >= 1, "k_step should be >= 1");
@@ -647,12 +837,45 @@ int pgeof_compute_features_optimal(const float* xyz, size_t n_xyz, const uint32_
     if (n_rows == 0) return PGEOF_OK;
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
     CsrOnDevice d;
-    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, n_rows, n_rows * 12, s));
-    PGEOF_TRY(features_optimal_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.ptr.as<uint32_t>(), n_rows, k_min, k_step,
+    PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_rows * 12, s));
+    PGEOF_TRY(features_optimal_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.dptr, n_rows, k_min, k_step,
                                    k_min_search, eig_order, d.out.as<float>(), s));
     PGEOF_TRY(d2h(out, d.out, n_rows * 12 * 4, s));
     PGEOF_CUDA(cudaStreamSynchronize(s));
     return PGEOF_OK;
+}
+
+int pgeof_compute_features(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+                           uint32_t k_min, int eig_order, float* out)
+{
+    return features_host_core(xyz, n_xyz, nn, nnz, nn_ptr, 4, n_rows, k_min, eig_order, out);
+}
+int pgeof_compute_features_p64(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint64_t* nn_ptr, size_t n_rows,
+                               uint32_t k_min, int eig_order, float* out)
+{
+    return features_host_core(xyz, n_xyz, nn, nnz, nn_ptr, 8, n_rows, k_min, eig_order, out);
+}
+
+int pgeof_compute_features_multiscale(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+                                      size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out)
+{
+    return multiscale_host_core(xyz, n_xyz, nn, nnz, nn_ptr, 4, n_rows, k_scales, n_scales, eig_order, out);
+}
+int pgeof_compute_features_multiscale_p64(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint64_t* nn_ptr,
+                                          size_t n_rows, const uint32_t* k_scales, size_t n_scales, int eig_order, float* out)
+{
+    return multiscale_host_core(xyz, n_xyz, nn, nnz, nn_ptr, 8, n_rows, k_scales, n_scales, eig_order, out);
+}
+
+int pgeof_compute_features_optimal(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+                                   uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out)
+{
+    return optimal_host_core(xyz, n_xyz, nn, nnz, nn_ptr, 4, n_rows, k_min, k_step, k_min_search, eig_order, out);
+}
+int pgeof_compute_features_optimal_p64(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint64_t* nn_ptr, size_t n_rows,
+                                       uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out)
+{
+    return optimal_host_core(xyz, n_xyz, nn, nnz, nn_ptr, 8, n_rows, k_min, k_step, k_min_search, eig_order, out);
 }
 
 // ------------------------------- selected ----------------------------------

@@ -125,15 +125,24 @@ enum SearchMode { SEARCH_KNN = 0, SEARCH_RADIUS = 1, SEARCH_RADIUS_COUNT = 2, SE
 int search_run(SearchMode mode, const float* data, size_t n_data, const float* query, size_t n_query, uint32_t k,
                float radius, void* indices, float* sqr_dist, uint32_t* nn_ptr, cudaStream_t stream);
 
-int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+// CSR row offsets: uint32 as in the reference (pgeof.hpp:78-79) or uint64 (extension beyond 2^32-1 neighbours)
+struct RowPtr {
+    const uint32_t* p32 = nullptr;
+    const unsigned long long* p64 = nullptr;
+    RowPtr(const uint32_t* p) : p32(p) {}
+    RowPtr(const unsigned long long* p) : p64(p) {}
+    RowPtr(const uint32_t* a, const unsigned long long* b) : p32(a), p64(b) {}
+};
+
+int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr, size_t n_rows,
                  uint32_t k_min, int eig_order, float* out, cudaStream_t stream, const uint32_t* out_rows = nullptr);
 // knn_search(xyz, xyz, knn) + compute_features without materialising the neighbour lists (fused knn_features extension);
 // *done = 0 if the fused path declined (the caller then runs the two kernels)
 int knn_features_fused_run(const float* xyz, size_t n, uint32_t knn, uint32_t k_min, int eig_order, float* features, cudaStream_t stream, int* done);
-int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr,
                             size_t n_rows, const uint32_t* k_scales_host, size_t n_scales, int eig_order, float* out,
                             cudaStream_t stream);
-int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr,
                          size_t n_rows, uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out,
                          cudaStream_t stream);
 int selected_run_f32(const float* xyz, size_t n, float radius, uint32_t max_knn, const int32_t* ids_host, size_t n_ids,

@@ -41,8 +41,10 @@ struct FeatArgs {
     const float4* pts;            // the cloud as 16-B records: Morton order when `rank` is set, input order otherwise
     const uint32_t* rank;         // original index -> position in pts, or nullptr = identity
     const uint32_t* order;        // spatial row permutation, or nullptr = identity
-    const uint32_t* nn; uint32_t nnz;
-    const uint32_t* nn_ptr; uint32_t n_rows;
+    const uint32_t* nn; unsigned long long nnz;
+    const uint32_t* nn_ptr;                // row offsets, uint32 (the reference's dtype) ...
+    const unsigned long long* nn_ptr64;    // ... or uint64 (extension: more than 2^32-1 neighbours in one CSR, README "known limitations")
+    uint32_t n_rows;
     uint32_t k_min; int eig_order;
     float* out;
     int* err;
@@ -107,6 +109,13 @@ __device__ __forceinline__ void stream_nn8(const uint32_t* p, uint32_t (&i)[8])
                  : "=r"(i[0]), "=r"(i[1]), "=r"(i[2]), "=r"(i[3]), "=r"(i[4]), "=r"(i[5]), "=r"(i[6]), "=r"(i[7]) : "l"(p));
 }
 
+// nn[b, e) of a row, whichever width the offsets have
+__device__ __forceinline__ void row_span(const FeatArgs& a, uint32_t row, unsigned long long& b, unsigned long long& e)
+{
+    if (a.nn_ptr64) { b = __ldg(a.nn_ptr64 + row); e = __ldg(a.nn_ptr64 + row + 1); }
+    else { b = __ldg(a.nn_ptr + row); e = __ldg(a.nn_ptr + row + 1); }
+}
+
 // position of neighbour `i` in the record array (the rank table turns the caller's index into the Morton position)
 __device__ __forceinline__ uint32_t record_of(const FeatArgs& a, uint32_t i) { return a.rank ? __ldg(a.rank + i) : i; }
 
@@ -132,7 +141,7 @@ __device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __r
 
 // acc(j, dx, dy, dz) is called for j = 0 .. len-1 in order, offsets relative to the row's first neighbour
 template <typename Acc>
-__device__ __forceinline__ bool walk_direct(const FeatArgs& a, uint32_t b, uint32_t len, Acc& acc)
+__device__ __forceinline__ bool walk_direct(const FeatArgs& a, unsigned long long b, uint32_t len, Acc& acc)
 {
     const uint32_t* __restrict__ p = a.nn + b;
     const uint32_t n = a.n_xyz;
@@ -184,13 +193,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
         if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
         s_rowid[threadIdx.x] = (a.out_rows && threadIdx.x < t.rows) ? __ldg(a.out_rows + row) : row;
         if (threadIdx.x < t.rows) {
-            const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
-            if (e < b || e > a.nnz) atomicExch(a.err, 1);        // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
+            unsigned long long b, e;
+            row_span(a, row, b, e);
+            if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);   // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
             else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
                 Moments m;
                 auto acc = [&](uint32_t, float dx, float dy, float dz) { m.add(dx, dy, dz); };
-                if (!walk_direct(a, b, e - b, acc)) atomicExch(a.err, 2);
-                else features11<float>(m.pca(e - b, a.eig_order), f);
+                if (!walk_direct(a, b, (uint32_t)(e - b), acc)) atomicExch(a.err, 2);
+                else features11<float>(m.pca((uint32_t)(e - b), a.eig_order), f);
             }
         }
 #pragma unroll
@@ -226,11 +236,12 @@ __global__ void __launch_bounds__(kMsThreads, 3) multiscale_direct_kernel(const 
     if (a.order) row = __ldg(a.order + row);
     float* out = a.out + ((size_t)row * a.n_scales_total + a.scale_base) * 11;
     const float zero[11] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
+    unsigned long long b, e;
+    row_span(a, row, b, e);
     uint32_t n_fit = 0, s = 0;                                  // scales of this pass the row is long enough for / written so far
-    if (e < b || e > a.nnz) atomicExch(a.err, 1);
+    if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);
     else {
-        const uint32_t len = e - b;
+        const uint32_t len = (uint32_t)(e - b);
         while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
         if (n_fit && a.scales[n_fit - 1] > 0) {
             Moments m;
@@ -311,10 +322,11 @@ __global__ void __launch_bounds__(kRows, 4) optimal_direct_kernel(const FeatArgs
     if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
     s_rowid[threadIdx.x] = row;
     if (threadIdx.x < t.rows) {
-        const uint32_t b = __ldg(a.nn_ptr + row), e = __ldg(a.nn_ptr + row + 1);
-        if (e < b || e > a.nnz) atomicExch(a.err, 1);
+        unsigned long long b, e;
+        row_span(a, row, b, e);
+        if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);
         else {
-            const uint32_t len = e - b;
+            const uint32_t len = (uint32_t)(e - b);
             if (len >= a.k_min && len >= a.k_min_search && len > 0) {                     // pgeof.hpp:272
                 const uint32_t k0 = min(max(max(a.k_min, a.k_min_search), 1u), len);    // :274
                 MomentsD m;
@@ -449,7 +461,8 @@ __global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const 
     const bool valid = i < a.n_rows;
     uint32_t key = 0;
     if (valid) {
-        const uint32_t b = __ldg(a.nn_ptr + i), e = __ldg(a.nn_ptr + i + 1);
+        unsigned long long b, e;
+        row_span(a, i, b, e);
         if (e > b && b < a.nnz) {
             const uint32_t first = __ldg(a.nn + b);
             if (first < a.n_xyz) key = __ldg(point_keys + first);
@@ -466,13 +479,14 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(uint32_t n_rows, const
     if (i < n_rows) order[__ldg(starts + keys[i]) + rank[i]] = i;
 }
 
-int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr, size_t n_rows,
               int eig_order, float* out, int* err)
 {
-    if (n_xyz > 0xffffffffull || nnz > 0xffffffffull || n_rows > 0xfffffffeull) { set_error("array too large for uint32 CSR"); return PGEOF_EINVAL; }
+    if (n_xyz > 0xffffffffull || n_rows > 0xfffffffeull) { set_error("more than 2^32-1 points or rows"); return PGEOF_EINVAL; }
+    if (!nn_ptr.p64 && nnz > 0xffffffffull) { set_error("nn holds more than 2^32-1 entries: uint32 nn_ptr cannot address them (pass uint64 offsets or shard the rows)"); return PGEOF_EINVAL; }
     if (eig_order != PGEOF_EIG_LITERAL && eig_order != PGEOF_EIG_DOCUMENTED) { set_error("bad eig_order %d", eig_order); return PGEOF_EINVAL; }
     std::memset(a, 0, sizeof(*a));
-    a->n_xyz = (uint32_t)n_xyz; a->nn = nn; a->nnz = (uint32_t)nnz; a->nn_ptr = nn_ptr; a->n_rows = (uint32_t)n_rows;
+    a->n_xyz = (uint32_t)n_xyz; a->nn = nn; a->nnz = nnz; a->nn_ptr = nn_ptr.p32; a->nn_ptr64 = nn_ptr.p64; a->n_rows = (uint32_t)n_rows;
     a->eig_order = eig_order; a->out = out; a->err = err; a->k_min = 1; a->k_step = 1; a->k_min_search = 1;
     a->tma_out = ((uintptr_t)out % 16 == 0);
     return PGEOF_OK;
@@ -534,11 +548,17 @@ int prepare(FeatArgs* a, const float* xyz, Prepass* p, cudaStream_t stream)
     PGEOF_LAUNCH_CHECK();
     PGEOF_TRY(exclusive_scan_u32(pc, n_cells, stream));
     PGEOF_TRY(exclusive_scan_u32(rc, n_cells, stream));
-    point_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, pc, pkeys.as<uint32_t>(), p->rank.as<uint32_t>(), p->pts.as<float4>());
-    PGEOF_LAUNCH_CHECK();
+    // PGEOF_FEATURES_RANK = 0: rows in spatial order, cloud left in input order (the round-1 layout; A/B switch)
+    if (env_int("PGEOF_FEATURES_RANK", 1) != 0) {
+        point_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, pc, pkeys.as<uint32_t>(), p->rank.as<uint32_t>(), p->pts.as<float4>());
+        PGEOF_LAUNCH_CHECK();
+        a->rank = p->rank.as<uint32_t>();
+    } else {
+        pad_xyz_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, p->pts.as<float4>());
+        PGEOF_LAUNCH_CHECK();
+    }
     row_scatter_kernel<<<rblocks, 256, 0, stream>>>(a->n_rows, rc, keys.as<uint32_t>(), rrank.as<uint32_t>(), p->order.as<uint32_t>());
     PGEOF_LAUNCH_CHECK();
-    a->rank = p->rank.as<uint32_t>();
     a->order = p->order.as<uint32_t>();
     return PGEOF_OK;
 }
@@ -555,7 +575,7 @@ int device_flag_check(const int* d_flag, cudaStream_t stream, const char* what)
     return PGEOF_OK;
 }
 
-int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr, size_t n_rows,
+int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr, size_t n_rows,
                  uint32_t k_min, int eig_order, float* out, cudaStream_t stream, const uint32_t* out_rows)
 {
     if (n_rows == 0) return PGEOF_OK;
@@ -584,7 +604,7 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
     return device_flag_check(err.as<int>(), stream, "compute_features");
 }
 
-int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr,
                             size_t n_rows, const uint32_t* k_scales_host, size_t n_scales, int eig_order, float* out,
                             cudaStream_t stream)
 {
@@ -610,7 +630,7 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
     return device_flag_check(err.as<int>(), stream, "compute_features_multiscale");
 }
 
-int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const uint32_t* nn_ptr,
+int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr,
                          size_t n_rows, uint32_t k_min, uint32_t k_step, uint32_t k_min_search, int eig_order, float* out,
                          cudaStream_t stream)
 {

@@ -188,3 +188,19 @@ def test_reference_arm_maps_no_product_library():
             "assert 'point_geometric_features_b200' not in sys.modules\n") % os.path.join(root, "bench.py")
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
+
+
+def test_type_stub_and_marker_match_the_module():
+    """Packaging parity (reference CMakeLists.txt:34-41 ships pgeof_ext.pyi + py.typed): the hand-written stub names exactly
+    what the compiled module exports."""
+    import ast
+    import point_geometric_features_b200.pgeof_ext as ext
+    pkg = os.path.dirname(ext.__file__)
+    root = os.path.dirname(pkg)
+    assert os.path.exists(os.path.join(pkg, "py.typed")) and os.path.exists(os.path.join(root, "pgeof", "py.typed"))
+    tree = ast.parse(open(os.path.join(pkg, "pgeof_ext.pyi")).read())
+    names = {n.name for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef))} | {n.target.id for n in tree.body if isinstance(n, ast.AnnAssign)}
+    assert names == {n for n in dir(ext) if not n.startswith("_")}
+    enum_cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "EFeatureID"][0]
+    members = {n.targets[0].id: n.value.value for n in enum_cls.body if isinstance(n, ast.Assign)}
+    assert members == {k: int(v) for k, v in ext.EFeatureID.__members__.items()}

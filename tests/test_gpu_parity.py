@@ -595,7 +595,7 @@ def test_optimal_k_against_the_float32_arithmetic_of_the_reference():
 
 
 SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"),
-            ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0")]
+            ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_RANK", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0")]
 
 
 @pytest.mark.parametrize("name,value", SWITCHES)
@@ -653,3 +653,80 @@ def test_slab_shards_from_the_library_match_the_host_restatement():
                 assert rows_d.dtype == torch.int64 and torch.equal(rows_d.cpu(), rows_h) and torch.equal(q_d.cpu(), q_h)
                 total += rows_h.shape[0]
             assert total == len(xyz)
+
+
+def test_csr_native_outputs_and_wide_offsets(monkeypatch):
+    """knn_search_csr / radius_search_csr emit what the README glue builds; nn_ptr may be 64-bit."""
+    import torch
+    xyz = dense_lidar(150000, seed=8)
+    idx, _ = cpu.knn_search(xyz, xyz, 17)
+    nn_ref, ptr_ref = knn_csr(idx)
+    for wide in (False, True):
+        nn, ptr = b200.knn_search_csr(xyz, xyz, 17, wide)
+        assert nn.dtype == np.uint32 and ptr.dtype == (np.uint64 if wide else np.uint32)
+        np.testing.assert_array_equal(nn, nn_ref)
+        np.testing.assert_array_equal(ptr.astype(np.uint64), ptr_ref.astype(np.uint64))
+        t = torch.from_numpy(xyz).cuda()
+        nn_t, ptr_t = b200.knn_search_csr(t, t, 17, wide)
+        assert ptr_t.dtype == (torch.int64 if wide else torch.uint32)
+        np.testing.assert_array_equal(nn_t.cpu().numpy(), nn_ref)
+        # the feature functions take either width and give bit-identical rows
+        f32 = pgeof.compute_features(xyz, nn_ref, ptr_ref)
+        np.testing.assert_array_equal(pgeof.compute_features(xyz, nn, ptr), f32)
+        np.testing.assert_array_equal(pgeof.compute_features(t, nn_t, ptr_t).cpu().numpy(), f32)
+        np.testing.assert_array_equal(pgeof.compute_features_multiscale(xyz, nn, ptr, [5, 17]), pgeof.compute_features_multiscale(xyz, nn_ref, ptr_ref, [5, 17]))
+        np.testing.assert_array_equal(pgeof.compute_features_optimal(xyz, nn, ptr, 1, 1, 4), pgeof.compute_features_optimal(xyz, nn_ref, ptr_ref, 1, 1, 4))
+    # radius CSR: one search for the call pair (parked padded table) == the two-pass count + fill == README glue on the padded result
+    ridx, _ = cpu.radius_search(xyz, xyz[:40000], 0.25, 48)
+    nn_ref, ptr_ref = radius_csr(ridx)
+    for two_pass in (False, True):
+        if two_pass:
+            monkeypatch.setenv("PGEOF_RADIUS_CSR_TWO_PASS", "1")
+        for a, q in ((xyz, xyz[:40000]), (torch.from_numpy(xyz).cuda(), torch.from_numpy(xyz[:40000]).cuda())):
+            nn, ptr = b200.radius_search_csr(a, q, 0.25, 48)
+            nn, ptr = (nn.cpu().numpy(), ptr.cpu().numpy()) if hasattr(nn, "cpu") else (nn, ptr)
+            np.testing.assert_array_equal(ptr, ptr_ref)
+            np.testing.assert_array_equal(nn, nn_ref)
+    with pytest.raises(IndexError):
+        pgeof.compute_features(xyz, nn_ref, np.array([0, 2 ** 33], np.uint64))
+
+
+def test_torch_adaptor_frnn_and_spt_helpers_against_brute_force():
+    """FRNN-shaped batched fixed-radius search and SuperPoint-Transformer style knn_1 / knn_2 (nn_search.hpp:72)."""
+    import torch
+    from point_geometric_features_b200 import torch_adaptor as ta
+    g = torch.Generator().manual_seed(5)
+    N, P1, P2, K, r = 3, 700, 900, 12, 0.17
+    p1, p2 = torch.rand(N, P1, 3, generator=g).cuda(), torch.rand(N, P2, 3, generator=g).cuda()
+    l1, l2 = torch.tensor([700, 433, 1]).cuda(), torch.tensor([900, 10, 512]).cuda()
+    dists, idxs, nn, grid = ta.frnn_grid_points(p1, p2, l1, l2, K=K, r=r, return_nn=True)
+    assert dists.shape == (N, P1, K) and idxs.dtype == torch.int64 and nn.shape == (N, P1, K, 3) and grid is None
+    for n in range(N):
+        a, b = p1[n, :l1[n]], p2[n, :l2[n]]
+        diff = a[:, None, :] - b[None, :, :]
+        d2 = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]      # the defined float32 metric
+        d2 = torch.where(d2 < torch.tensor(r, dtype=torch.float32).cuda() ** 2, d2, torch.full_like(d2, float("inf")))
+        order = torch.argsort(d2, dim=1, stable=True)[:, :K]                                                # ties by index
+        ref_d = torch.gather(d2, 1, order)
+        kk = order.shape[1]
+        ref_i = torch.where(torch.isinf(ref_d), torch.full_like(order, -1), order)
+        ref_d = torch.where(torch.isinf(ref_d), torch.full_like(ref_d, -1.0), ref_d)
+        assert torch.equal(idxs[n, :l1[n], :kk], ref_i) and torch.equal(dists[n, :l1[n], :kk], ref_d)
+        assert bool((idxs[n, :l1[n], kk:] == -1).all()) and bool((idxs[n, l1[n]:] == -1).all()) and bool((dists[n, l1[n]:] == -1).all())
+        hit = idxs[n, :l1[n]] >= 0
+        assert torch.equal(nn[n, :l1[n]][hit], b[idxs[n, :l1[n]][hit]])
+    # SPT helpers on a flat cloud with a sorted batch vector
+    xyz = torch.cat([p2[0], p2[2, :512] + 5.0])
+    batch = torch.cat([torch.zeros(900, dtype=torch.int64), torch.ones(512, dtype=torch.int64)]).cuda()
+    nb, ds = ta.knn_1(xyz, 8, r_max=0.2, batch=batch)
+    assert nb.shape == (1412, 8) and ds.shape == (1412, 8)
+    assert bool((nb[:900][nb[:900] >= 0] < 900).all()) and bool((nb[900:][nb[900:] >= 0] >= 900).all())    # no neighbour across clouds
+    assert bool((nb != torch.arange(1412, device="cuda")[:, None]).all())                                   # self dropped
+    full = torch.cdist(xyz[:900].double(), xyz[:900].double())
+    full.fill_diagonal_(float("inf"))
+    ref = torch.sort(full, dim=1).values[:, :8]
+    got = ds[:900].double()
+    ok = got >= 0
+    assert torch.allclose(got[ok], ref[ok], atol=1e-6) and bool((ref[~ok] >= 0.2 - 1e-6).all())
+    nb2, ds2 = ta.knn_2(xyz, xyz[:50], 5, r_max=10.0)
+    assert bool((nb2[:, 0] == torch.arange(50, device="cuda")).all()) and bool((ds2[:, 0] == 0).all())
