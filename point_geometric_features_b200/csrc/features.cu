@@ -2,21 +2,21 @@
 // Replaces compute_geometric_features{,_multiscale,_optimal} (include/pgeof.hpp:75-310)
 // and pca_from_neighborhood / pca_from_pointcloud (include/pca.hpp:71-129).
 //
-// Layout.  Two counting sorts on one coarse Morton grid make the gathers coherent:
-//   * the CLOUD is copied once into 16-B float4 records ordered by the Morton code of their coarse
-//     cell (`pts`), with a rank table `rank[original index] = position in pts` (4 B per point: 40 MB
-//     for 10 M points, resident in the 126 MB L2 where the 160 MB float4 cloud is not).  A gather is
-//     rank[nn[j]] (a random 4-B read served by L2) followed by ONE 128-bit load of a record whose
-//     128-B line is shared with the neighbourhoods of the rows around it.  The first version gathered
-//     from the cloud in input order: every neighbour sat in its own line, 6.1 GB of DRAM reads for
-//     2.2 GB compulsory (profiles/r1c_summary.md);
-//   * the ROWS are processed in the same order (key = cell of the row's first neighbour), so that
-//     consecutive threads / CTAs work on overlapping neighbourhoods.
-// One CTA owns a tile of rows, ONE THREAD PER ROW: every thread streams its own slice of `nn` with
-// 256-bit no-allocate loads (the stream is read exactly once and must not crowd the gathered points
-// out of L1), keeps 8 gathers in flight, accumulates the 9 origin-shifted moments (origin = the row's
-// first neighbour), solves the 3x3 eigenproblem in registers (eig3.cuh) and the tile's
-// features leave through shared memory as 44-B row segments (permuted rows) or one TMA bulk store.
+// Layout.  Rows are processed in SPATIAL order: a counting sort of the rows by the Morton code of the coarse
+// cell of their first neighbour makes consecutive threads / CTAs work on overlapping neighbourhoods, so the gathers
+// of a row hit lines its spatial neighbours just pulled into L1 / L2.  The cloud is re-packed once into 16-B float4
+// records so that a gather is ONE 128-bit load.  One CTA owns a tile of rows, ONE THREAD PER ROW: every thread
+// streams its own slice of `nn` with 256-bit no-allocate loads (the stream is read exactly once and must not crowd
+// the gathered points out of L1), keeps 8 gathers in flight, accumulates the 9 origin-shifted moments (origin = the
+// row's first neighbour), solves the 3x3 eigenproblem in registers (eig3.cuh) and the tile's features
+// leave through shared memory as 44-B row segments (permuted rows) or one TMA bulk store.
+//
+// What bounds it (profiles/r2_summary.md): not HBM.  Every gather of a warp instruction goes to a different 128-B
+// line (32 rows x their j-th neighbour), i.e. 32 L1 tag wavefronts per instruction: 5.6e8 wavefronts per 10 M x 50
+// launch = 2.0 ms at one wavefront per clock per SM; the kernel runs at ~73 % of that rate and its time does not move
+// when the DRAM traffic is changed by 60 % with L2 policies.  A Morton-sorted copy of the cloud behind a rank table
+// (rank[nn[j]] then the record) was built and measured in round 2: DRAM reads 6.1 -> 5.6 GB, but the table lookups
+// are as scattered as the gathers they replace -- same time, +0.3 ms of pre-pass -- and dropped.
 //
 // Algorithmic bytes per row of length k: 4k (nn) + 4 (nn_ptr) + 12k (xyz gather) + 44 (out)
 // = 48 + 16k.
@@ -38,8 +38,7 @@ constexpr int kMaxScalesPerPass = 8;
 
 struct FeatArgs {
     uint32_t n_xyz;
-    const float4* pts;            // the cloud as 16-B records: Morton order when `rank` is set, input order otherwise
-    const uint32_t* rank;         // original index -> position in pts, or nullptr = identity
+    const float4* pts;            // the cloud as 16-B float4 records (input order): one LDG.128 per gather
     const uint32_t* order;        // spatial row permutation, or nullptr = identity
     const uint32_t* nn; unsigned long long nnz;
     const uint32_t* nn_ptr;                // row offsets, uint32 (the reference's dtype) ...
@@ -116,9 +115,6 @@ __device__ __forceinline__ void row_span(const FeatArgs& a, uint32_t row, unsign
     else { b = __ldg(a.nn_ptr + row); e = __ldg(a.nn_ptr + row + 1); }
 }
 
-// position of neighbour `i` in the record array (the rank table turns the caller's index into the Morton position)
-__device__ __forceinline__ uint32_t record_of(const FeatArgs& a, uint32_t i) { return a.rank ? __ldg(a.rank + i) : i; }
-
 // up to N (<= 7) consecutive entries: indices first, then their gathers together, then the moments in order
 template <int N, typename Acc>
 __device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __restrict__ p, uint32_t j0, uint32_t cnt, uint32_t i0, const float4& o,
@@ -131,8 +127,6 @@ __device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __r
         i[u] = (uint32_t)u < cnt ? __ldg(p + u) : i0;
         if (i[u] >= a.n_xyz) { ok = false; i[u] = i0; }
     }
-#pragma unroll
-    for (int u = 0; u < N; ++u) i[u] = record_of(a, i[u]);
 #pragma unroll
     for (int u = 0; u < N; ++u) q[u] = __ldg(a.pts + i[u]);
 #pragma unroll
@@ -147,7 +141,7 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, unsigned long lon
     const uint32_t n = a.n_xyz;
     const uint32_t i0 = __ldg(p);
     if (i0 >= n) return false;
-    const float4 o = __ldg(a.pts + record_of(a, i0));   // origin of the shifted moments; its own term is zero
+    const float4 o = __ldg(a.pts + i0);   // origin of the shifted moments; its own term is zero
     bool ok = true;
     acc(0u, 0.f, 0.f, 0.f);
     uint32_t j = 1;
@@ -160,8 +154,6 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, unsigned long lon
         float4 q[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) if (i[u] >= n) { ok = false; i[u] = i0; }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) i[u] = record_of(a, i[u]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) q[u] = __ldg(a.pts + i[u]);
 #pragma unroll
@@ -428,33 +420,8 @@ __device__ __forceinline__ uint32_t bucket_rank(uint32_t* __restrict__ counts, u
     return base + (uint32_t)__popc(peers & lt);
 }
 
-__global__ void __launch_bounds__(256) point_count_kernel(const float* __restrict__ xyz, uint32_t n, const RowGrid* __restrict__ gp,
-                                                          uint32_t* __restrict__ counts, uint32_t* __restrict__ keys, uint32_t* __restrict__ rank)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
-    uint32_t key = 0;
-    if (valid) {
-        const RowGrid g = *gp;
-        key = morton_key(g, __ldg(xyz + 3 * (size_t)i), __ldg(xyz + 3 * (size_t)i + 1), __ldg(xyz + 3 * (size_t)i + 2));
-    }
-    const uint32_t r = bucket_rank(counts, key, valid);
-    if (valid) { keys[i] = key; rank[i] = r; }
-}
-
-// pts[start[key] + rank] = record of point i; rank[i] becomes the record's position (the gather table)
-__global__ void __launch_bounds__(256) point_scatter_kernel(const float* __restrict__ xyz, uint32_t n, const uint32_t* __restrict__ starts,
-                                                            const uint32_t* __restrict__ keys, uint32_t* __restrict__ rank, float4* __restrict__ pts)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t pos = __ldg(starts + keys[i]) + rank[i];
-    pts[pos] = make_float4(__ldg(xyz + 3 * (size_t)i), __ldg(xyz + 3 * (size_t)i + 1), __ldg(xyz + 3 * (size_t)i + 2), 0.f);
-    rank[i] = pos;
-}
-
 // a row sorts with the cell of its first neighbour (itself, for the rows of a self kNN / radius search)
-__global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const uint32_t* __restrict__ point_keys, uint32_t* __restrict__ counts,
+__global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const RowGrid* __restrict__ gp, uint32_t* __restrict__ counts,
                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ rank)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,7 +432,10 @@ __global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const 
         row_span(a, i, b, e);
         if (e > b && b < a.nnz) {
             const uint32_t first = __ldg(a.nn + b);
-            if (first < a.n_xyz) key = __ldg(point_keys + first);
+            if (first < a.n_xyz) {
+                const float4 p = __ldg(a.pts + first);
+                key = morton_key(*gp, p.x, p.y, p.z);
+            }
         }
     }
     const uint32_t r = bucket_rank(counts, key, valid);
@@ -477,6 +447,12 @@ __global__ void __launch_bounds__(256) row_scatter_kernel(uint32_t n_rows, const
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_rows) order[__ldg(starts + keys[i]) + rank[i]] = i;
+}
+
+int env_int(const char* name, int dflt)
+{
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
 }
 
 int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr, size_t n_rows,
@@ -494,70 +470,45 @@ int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr 
 
 // Device buffers of the pre-passes; they live until the feature kernel was enqueued (stream-ordered frees).
 struct Prepass {
-    DeviceBuffer pts, rank, order;
+    DeviceBuffer pts, order;
 };
 
-int env_int(const char* name, int dflt)
-{
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
-}
-
-// PGEOF_FEATURES_SORT = 0 keeps the cloud and the rows in input order (debugging / small inputs do that anyway)
+// PGEOF_FEATURES_SORT = 0 keeps the rows in input order (debugging; small inputs do that anyway)
 int prepare(FeatArgs* a, const float* xyz, Prepass* p, cudaStream_t stream)
 {
     const uint32_t n = a->n_xyz;
+    // 1. float4 re-pack of the cloud: one 128-bit load per gathered neighbour
     PGEOF_TRY(p->pts.alloc((size_t)std::max<uint32_t>(n, 1) * sizeof(float4), stream));
     a->pts = p->pts.as<float4>();
-    const int min_rows = env_int("PGEOF_FEATURES_SORT_MIN_ROWS", 32768);
-    const bool sort = n != 0 && a->nnz != 0 && (int64_t)a->n_rows >= (int64_t)min_rows && env_int("PGEOF_FEATURES_SORT", 1) != 0;
-    if (!sort) {
-        if (n) {
-            pad_xyz_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, p->pts.as<float4>());
-            PGEOF_LAUNCH_CHECK();
-        }
-        return PGEOF_OK;
+    if (n) {
+        pad_xyz_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, p->pts.as<float4>());
+        PGEOF_LAUNCH_CHECK();
     }
+    // 2. spatial row order (counting sort by the Morton cell of the first neighbour)
+    const int min_rows = env_int("PGEOF_FEATURES_SORT_MIN_ROWS", 32768);
+    if (n == 0 || a->nnz == 0 || (int64_t)a->n_rows < (int64_t)min_rows || env_int("PGEOF_FEATURES_SORT", 1) == 0) return PGEOF_OK;
     KernelTimer timer("row_order", stream);
-    DeviceBuffer partial, grid, counts, keys, pkeys, rrank;
+    DeviceBuffer partial, grid, counts, keys, rrank;
     int n_partial = 0;
     PGEOF_TRY(bbox_partials(xyz, n, &partial, &n_partial, stream));
-    int cells = (int)std::lround(std::cbrt((double)std::max<uint32_t>(n, a->n_rows) / 6.0));
+    int cells = (int)std::lround(std::cbrt((double)a->n_rows / 6.0));
     cells = std::min(std::max(cells, 8), 128);
     int bits = 3;
     while ((1 << bits) < cells) ++bits;
     const size_t n_cells = (size_t)1 << (3 * bits);
     PGEOF_TRY(grid.alloc(sizeof(RowGrid), stream));
-    PGEOF_TRY(counts.alloc(2 * (n_cells + 1) * sizeof(uint32_t), stream));      // point histogram | row histogram
-    PGEOF_TRY(pkeys.alloc((size_t)n * sizeof(uint32_t), stream));
-    PGEOF_TRY(p->rank.alloc((size_t)n * sizeof(uint32_t), stream));
+    PGEOF_TRY(counts.alloc((n_cells + 1) * sizeof(uint32_t), stream));
     PGEOF_TRY(keys.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     PGEOF_TRY(rrank.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
     PGEOF_TRY(p->order.alloc((size_t)a->n_rows * sizeof(uint32_t), stream));
-    uint32_t* pc = counts.as<uint32_t>();
-    uint32_t* rc = pc + n_cells + 1;
     row_grid_kernel<<<1, 32, 0, stream>>>(partial.as<float>(), n_partial, cells, grid.as<RowGrid>());
     PGEOF_LAUNCH_CHECK();
-    PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, 2 * (n_cells + 1) * sizeof(uint32_t), stream));
-    // 1. the cloud: float4 records in Morton order + rank table
-    point_count_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, grid.as<RowGrid>(), pc, pkeys.as<uint32_t>(), p->rank.as<uint32_t>());
-    PGEOF_LAUNCH_CHECK();
-    // 2. the rows, by the cell of their first neighbour (needs only the point keys)
+    PGEOF_CUDA(cudaMemsetAsync(counts.ptr, 0, (n_cells + 1) * sizeof(uint32_t), stream));
     const unsigned rblocks = (a->n_rows + 255) / 256;
-    row_count_kernel<<<rblocks, 256, 0, stream>>>(*a, pkeys.as<uint32_t>(), rc, keys.as<uint32_t>(), rrank.as<uint32_t>());
+    row_count_kernel<<<rblocks, 256, 0, stream>>>(*a, grid.as<RowGrid>(), counts.as<uint32_t>(), keys.as<uint32_t>(), rrank.as<uint32_t>());
     PGEOF_LAUNCH_CHECK();
-    PGEOF_TRY(exclusive_scan_u32(pc, n_cells, stream));
-    PGEOF_TRY(exclusive_scan_u32(rc, n_cells, stream));
-    // PGEOF_FEATURES_RANK = 0: rows in spatial order, cloud left in input order (the round-1 layout; A/B switch)
-    if (env_int("PGEOF_FEATURES_RANK", 1) != 0) {
-        point_scatter_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, pc, pkeys.as<uint32_t>(), p->rank.as<uint32_t>(), p->pts.as<float4>());
-        PGEOF_LAUNCH_CHECK();
-        a->rank = p->rank.as<uint32_t>();
-    } else {
-        pad_xyz_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, p->pts.as<float4>());
-        PGEOF_LAUNCH_CHECK();
-    }
-    row_scatter_kernel<<<rblocks, 256, 0, stream>>>(a->n_rows, rc, keys.as<uint32_t>(), rrank.as<uint32_t>(), p->order.as<uint32_t>());
+    PGEOF_TRY(exclusive_scan_u32(counts.as<uint32_t>(), n_cells, stream));
+    row_scatter_kernel<<<rblocks, 256, 0, stream>>>(a->n_rows, counts.as<uint32_t>(), keys.as<uint32_t>(), rrank.as<uint32_t>(), p->order.as<uint32_t>());
     PGEOF_LAUNCH_CHECK();
     a->order = p->order.as<uint32_t>();
     return PGEOF_OK;

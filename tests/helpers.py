@@ -100,7 +100,20 @@ def compare_features(got, ref, evals, eig_order="literal", what="features", ids=
         for fid in (0, 1, 2, 10, 7, 8, 9):
             for c in col.get(fid, []):
                 bad[weak, c] = loose_lit[weak, c]
-                bad[deg, c] = loose_lit[deg, c]
+        # Rank-deficient rows: the one or two small singular values are pure round-off, anywhere in [0, d] with
+        # d = sqrt(4e-7 lambda_max) in a float32 evaluation (0 in float64).  Each column gets the tolerance that follows from
+        # its formula: the ratio features divide by (s0 + 1e-3) with s0 <= d; Length = s0; Surface = sqrt(s0 s1 + 1e-6);
+        # Volume = cbrt(s0 s1 s2 + 1e-9); Curvature = s2 / (s0 + s1 + s2 + 1e-3).
+        lmax = np.maximum(evals[:, 2], 0.0)
+        d = np.sqrt(4e-7 * lmax)
+        smax_ = np.sqrt(lmax)
+        deg_tol = {0: 2e3 * d, 1: 2e3 * d, 2: 2e3 * d, 7: 2.0 * d, 8: 2.0 * d + np.sqrt(d * smax_), 9: np.cbrt(d * lmax),
+                   10: 4.0 * d / np.maximum(smax_, 1e-300)}
+        for fid, extra_tol in deg_tol.items():
+            # the ratio features also scale with 1 / (s0 + 1e-3), s0 anywhere in [0, d]: a relative uncertainty of d / 1e-3
+            rel = 1e-2 + (2e3 * d if fid in (0, 1, 2) else 0.0)
+            for c in col.get(fid, []):
+                bad[deg, c] = (err[:, c] > 1e-3 + rel * np.abs(ref[:, c]) + extra_tol)[deg]
         for c in vec_cols:
             bad[deg & ~ill, c] = loose[deg & ~ill, c]
         # pca.hpp:184 computes VerticalityPGEOF only `if (val0 > 0)`: on a rank-deficient row the literal val0 = sqrt(lambda_min) is
