@@ -353,7 +353,11 @@ __device__ __forceinline__ uint32_t select_sort_network(uint32_t (&v)[NOUT + NEX
     return dropped;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS, int MODE, bool FUSED = false>
+// LOCK: the warps of a CTA enter the straight-line sections (key load + sorting network, exact rebuild) together, so that
+// one instruction-cache fill serves all of them (profiles/r2_summary.md: the GPC-level instruction cache runs at 93 % of
+// its request rate when every warp streams the 62 KB of straight-line code on its own)
+#define PGEOF_LOCK_BARRIER() do { if (LOCK) asm volatile("bar.sync 0;" ::: "memory"); } while (0)
+template <int NOUT, int NEXTRA, int NWARPS, int MODE, bool FUSED = false, bool LOCK = false>
 __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
 {
     static_assert(MODE == SEARCH_KNN || MODE == SEARCH_RADIUS, "tile kernel: kNN or padded radius search");
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
     uint32_t* list = reinterpret_cast<uint32_t*>(wsm + Cfg::STAGE_BYTES);
     uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + Cfg::STAGE_BYTES + Cfg::LIST_BYTES);
     const uint32_t base = (blockIdx.x * Cfg::WARPS + warp) * 32u;
-    if (base >= a.n_query) return;
+    if (!LOCK && base >= a.n_query) return;     // (LOCK: a warp without queries still meets the barriers)
     const uint32_t k = a.k;
     if (lane == 0) { ptx::mbarrier_init(bar, 1); ptx::fence_mbarrier_init(); }
     __syncwarp();
@@ -392,7 +396,8 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
     float* const s_rmul = s_hint + 32;       // this lane's factor on the density-seeded radius
     uint32_t* const s_retry = reinterpret_cast<uint32_t*>(s_hint + 64);   // bits 0-1: re-queues so far, bits 2-3: class (0 first try, 1 grow, 2 shrink)
     *s_hint = 0.f; *s_rmul = 1.f; *s_retry = 0u;
-    for (int pass = 0; remaining; ++pass) {
+    for (int pass = 0; LOCK ? __syncthreads_or(remaining != 0) != 0 : remaining != 0; ++pass) {
+        if (LOCK && !remaining) { PGEOF_LOCK_BARRIER(); PGEOF_LOCK_BARRIER(); continue; }
         // ---- the lanes of this pass: queries in the (y, z) cell row of the first remaining lane ----
         const int leader = __ffs(remaining) - 1;
         const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
@@ -403,6 +408,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         if (pass >= Cfg::MAX_PASSES) {
             slow |= active;
             if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
+            PGEOF_LOCK_BARRIER(); PGEOF_LOCK_BARRIER();
             continue;
         }
 
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             remaining |= active & ~keep;
             active = keep;
         }
-        if (!active) continue;
+        if (!active) { PGEOF_LOCK_BARRIER(); PGEOF_LOCK_BARRIER(); continue; }
 
         // ---- stage the region: one 1-D TMA bulk copy per row, all rows in flight at once ---------
         __syncwarp();
@@ -592,6 +598,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         uint32_t nvalid = 0;                   // radius mode: kept entries whose defined distance is < r^2
         {
             uint32_t v[NLOAD];
+            PGEOF_LOCK_BARRIER();
 #pragma unroll
             for (int i = 0; i < NLOAD; ++i) {
                 const uint32_t w = wbase[i * S];
@@ -599,6 +606,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             }
             __syncwarp();                      // the lists are dead: their memory becomes the d2 plane
             dropped = select_sort_network<NOUT, NEXTRA>(v);
+            PGEOF_LOCK_BARRIER();
             // rebuild the exact (d2, index) pairs in sorted order.  Keys that share their truncated
             // distance may be out of order: remember it, the row is repaired in shared memory below.
             // plane[i * S + lane] = i-th neighbour of this lane's row
@@ -814,6 +822,421 @@ __global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g,
 }
 
 // ---------------------------------------------------------------------------------------
+// TWO LANES PER QUERY, one warp per 16 cell-sorted queries: kNN with k <= 128
+// ---------------------------------------------------------------------------------------
+// The thread-per-query tile kernel above is pinned at 8 warps per SM twice over: 255 registers for its 96-key sorting
+// network and 28.6 KB of shared memory per warp.  Here a query owns the lane pair (q, q + 16):
+//   * the region of 16 queries is a third smaller than that of 32 and each lane scans every other staged candidate
+//     (one LDS.128 serves the two half warps), appending survivors to its own list;
+//   * each lane sorts NL keys (what one list holds beyond NL is loaded by the partner).  The LOW lane works on the
+//     bit-complemented keys, the high lane on the keys themselves, both ascending: one exchange v = max(v, ~partner's v)
+//     then leaves the NL smallest of the 2 NL keys in the low lane and the NL largest in the high lane, each as a
+//     "down then up" sequence in the lane's own domain -- which stays bitonic when padded with +inf to a power of two, so
+//     a pruned bitonic merge finishes the sort (a padded "up then down" sequence would not be bitonic);
+//   * ranks [HOUT, NL) move to the high lane with one shuffle each, so both lanes rebuild HOUT exact (d2, index) pairs;
+//   * rows leave through the same shared-memory transpose.
+// Exactness argument, fall-back lists and radius feedback are those of the tile kernel.
+template <int NL_, int HOUT_, int NWARPS_, int CMAX_>
+struct PairCfg {
+    static constexpr int NL = NL_;                 // keys a lane sorts: a query absorbs 2 NL survivors
+    static constexpr int HOUT = HOUT_;             // ranks a lane rebuilds: a row keeps KOUT = 2 HOUT >= k ranks
+    static constexpr int KOUT = 2 * HOUT;
+    static constexpr int NX = NL - HOUT;           // ranks [HOUT, NL) move from the low lane to the high lane
+    static constexpr int LMAX = NL + NL / 3;       // entries ONE list may hold (the partner sorts what exceeds NL)
+    static constexpr int SINK = 11;
+    static constexpr int LCAP = LMAX + 1 + SINK;
+    static constexpr int STRIDE = 33;
+    static constexpr int WARPS = NWARPS_;
+    static constexpr int CMAX = CMAX_;             // candidates staged per pass
+    static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
+    static constexpr int STAGE_BYTES = CMAX * 16;
+    static constexpr int BAR_BYTES = 16 + 3 * 128;
+    static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
+    static constexpr int MAX_PASSES = 12;
+    static constexpr int RETRY_MIN = 8;            // queries (half of the warp's 16) that must fail the same way before a group retry
+    static constexpr uint32_t SLOT_BITS = 10;
+    static constexpr uint32_t SLOT_MASK = (1u << SLOT_BITS) - 1;
+    static constexpr uint32_t PAD = ~SLOT_MASK;
+    static constexpr int VN = NL <= 32 ? 32 : (NL <= 64 ? 64 : 128);   // virtual (power of two) length of the networks
+    static_assert(CMAX % 16 == 0 && CMAX <= (1 << SLOT_BITS), "slot field too small");
+    static_assert(LIST_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "alignment");
+    static_assert(HOUT * STRIDE * 4 <= LIST_BYTES && HOUT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
+    static_assert((1 << SLOT_BITS) * 16 <= SMEM_WARP_BYTES, "a padded slot must stay inside the warp's shared memory");
+    static_assert(NX >= 0 && NX <= HOUT && 2 * HOUT - NL >= 0 && HOUT % 32 == 0 && (NX == 0 || HOUT <= 2 * NX), "rank split");
+};
+
+template <int NL, int HOUT, int NWARPS, int CMAX, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) knn_pair_kernel(const GridView g, const SearchArgs a)
+{
+    using Cfg = PairCfg<NL, HOUT, NWARPS, CMAX>;
+    constexpr int S = Cfg::STRIDE, KOUT = Cfg::KOUT, NX = Cfg::NX, MR = KOUT / 32;
+    extern __shared__ __align__(128) unsigned char smem_tile[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ql = lane & 15;                      // query of this lane within the warp
+    const uint32_t hi = (uint32_t)lane >> 4;       // 0: low lane (ranks [0, HOUT)), 1: high lane (ranks [HOUT, KOUT))
+    unsigned char* wsm = smem_tile + (size_t)warp * Cfg::SMEM_WARP_BYTES;
+    float4* stage = reinterpret_cast<float4*>(wsm);
+    uint32_t* list = reinterpret_cast<uint32_t*>(wsm + Cfg::STAGE_BYTES);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wsm + Cfg::STAGE_BYTES + Cfg::LIST_BYTES);
+    const uint32_t base = (blockIdx.x * Cfg::WARPS + warp) * 16u;
+    if (base >= a.n_query) return;
+    const uint32_t k = a.k;
+    if (lane == 0) { ptx::mbarrier_init(bar, 1); ptx::fence_mbarrier_init(); }
+    __syncwarp();
+    uint32_t parity = 0;
+
+    const bool valid = base + ql < a.n_query;
+    const float4 q4 = valid ? __ldg(a.queries + base + ql) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float qx = q4.x, qy = q4.y, qz = q4.z;
+    const uint32_t row = __float_as_uint(q4.w);
+    const int cqx = cell_coord(qx, g.lo[0], g.inv_hx, g.n[0]);
+    const int cqy = cell_coord(qy, g.lo[1], g.inv_h, g.n[1]);
+    const int cqz = cell_coord(qz, g.lo[2], g.inv_h, g.n[2]);
+    const uint32_t rowid = (uint32_t)cqz * (uint32_t)g.n[1] + (uint32_t)cqy;
+    const uint32_t cm = hi ? 0u : 0xffffffffu;     // the low lane sorts complemented keys
+
+    // every mask below is symmetric: bit q and bit q + 16 describe the same query
+    unsigned remaining = __ballot_sync(kFull, valid);
+    unsigned slow = 0, unsafe = 0;
+    float* const s_hint = reinterpret_cast<float*>(bar + 2) + lane;
+    float* const s_rmul = s_hint + 32;
+    uint32_t* const s_retry = reinterpret_cast<uint32_t*>(s_hint + 64);
+    *s_hint = 0.f; *s_rmul = 1.f; *s_retry = 0u;
+    for (int pass = 0; remaining; ++pass) {
+        const int leader = __ffs(remaining) - 1;
+        const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
+        const uint32_t cls = *s_retry >> 2;
+        const uint32_t lcls = __shfl_sync(kFull, cls, leader);
+        unsigned active = __ballot_sync(kFull, ((remaining >> lane) & 1u) && rowid == lrow && cls == lcls);
+        remaining &= ~active;
+        if (pass >= Cfg::MAX_PASSES) {
+            slow |= active;
+            if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active & 0xffffu));
+            continue;
+        }
+
+        // ---- region of the active queries; a region too large to stage is halved along x ---------
+        float R = 0.f;
+        uint32_t s = 0, len = 0, off = 0, C = 0, C16 = 0;
+        bool mine = false;
+        for (int split = 0;; ++split) {
+            mine = (active >> lane) & 1u;
+            const float xmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qx) : 0xffffffffu));
+            const float xmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qx) : 0u));
+            const float ymin = o2f(__reduce_min_sync(kFull, mine ? f2o(qy) : 0xffffffffu));
+            const float ymax = o2f(__reduce_max_sync(kFull, mine ? f2o(qy) : 0u));
+            const float zmin = o2f(__reduce_min_sync(kFull, mine ? f2o(qz) : 0xffffffffu));
+            const float zmax = o2f(__reduce_max_sync(kFull, mine ? f2o(qz) : 0u));
+            const int cxa = __reduce_min_sync(kFull, mine ? cqx : 0x7fffffff);
+            const int cxb = __reduce_max_sync(kFull, mine ? cqx : -1);
+            const int cy = __shfl_sync(kFull, cqy, leader), cz = __shfl_sync(kFull, cqz, leader);
+            {   // density and shape of the 3 x 3 block of (y, z) rows -> search radius (see knn_tile_kernel)
+                const int bx0 = max(cxa - g.xf, 0), bx1 = min(cxb + g.xf, g.n[0] - 1);
+                float c = 0.f;
+                if (lane < 9) {
+                    const int by = cy + lane % 3 - 1, bz = cz + lane / 3 - 1;
+                    if (by >= 0 && by < g.n[1] && bz >= 0 && bz < g.n[2]) {
+                        const uint32_t rb = ((uint32_t)bz * (uint32_t)g.n[1] + (uint32_t)by) * (uint32_t)g.n[0];
+                        c = (float)(__ldg(g.cell_start + rb + bx1 + 1) - __ldg(g.cell_start + rb + bx0));
+                    }
+                }
+                float s1 = c, s2 = c * c;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) { s1 += __shfl_xor_sync(kFull, s1, o); s2 += __shfl_xor_sync(kFull, s2, o); }
+                s1 = fmaxf(__shfl_sync(kFull, s1, 0), 1.f);
+                s2 = fmaxf(__shfl_sync(kFull, s2, 0), 1.f);
+                const float m = fminf(fmaxf(s1 * s1 / s2, 1.f), 9.f);
+                const float d = 1.f + log2f(m) * 0.6309298f;
+                const float rho = s1 / (m * (float)(bx1 - bx0 + 1) * g.hx * g.h * g.h);
+                const float T = a.target;
+                const float l3 = log2f(T / (4.18879f * rho)) * (1.f / 3.f);
+                const float l2 = log2f(T / (3.14159265f * rho * g.h)) * 0.5f;
+                const float l1 = log2f(T / (2.f * rho * g.h * g.h));
+                float lr = d >= 2.f ? (d - 2.f) * l3 + (3.f - d) * l2 : (d - 1.f) * l2 + (2.f - d) * l1;
+                if (a.flags & 1u) lr = log2f(T / (4.18879f * s1 / (9.f * (float)(bx1 - bx0 + 1) * g.hx * g.h * g.h))) * (1.f / 3.f);
+                const float rm = __uint_as_float(__reduce_max_sync(kFull, mine ? __float_as_uint(*s_rmul) : 0u));
+                R = exp2f(lr) * rm;
+            }
+            if (R > g.rmax_safe) { unsafe |= active; active = 0; break; }
+            const int cx0 = cell_coord(__fsub_rd(xmin, R), g.lo[0], g.inv_hx, g.n[0]);
+            const int cx1 = cell_coord(__fadd_ru(xmax, R), g.lo[0], g.inv_hx, g.n[0]);
+            const int cy0 = cell_coord(__fsub_rd(ymin, R), g.lo[1], g.inv_h, g.n[1]);
+            const int cy1 = cell_coord(__fadd_ru(ymax, R), g.lo[1], g.inv_h, g.n[1]);
+            const int cz0 = cell_coord(__fsub_rd(zmin, R), g.lo[2], g.inv_h, g.n[2]);
+            const int cz1 = cell_coord(__fadd_ru(zmax, R), g.lo[2], g.inv_h, g.n[2]);
+            const uint32_t nyr = (uint32_t)(cy1 - cy0 + 1);
+            const uint32_t nrows = nyr * (uint32_t)(cz1 - cz0 + 1);
+            bool fits = nrows <= 32u;
+            if (fits) {
+                s = 0; len = 0;
+                if ((uint32_t)lane < nrows) {
+                    const int rz = cz0 + (int)((uint32_t)lane / nyr), ry = cy0 + (int)((uint32_t)lane % nyr);
+                    const uint32_t rb = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
+                    s = __ldg(g.cell_start + rb + cx0);
+                    len = __ldg(g.cell_start + rb + cx1 + 1) - s;
+                }
+                off = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(kFull, off, o);
+                    if (lane >= o) off += t;
+                }
+                C = __shfl_sync(kFull, off, 31);
+                off -= len;
+                C16 = (C + 15u) & ~15u;
+                fits = C16 <= (uint32_t)Cfg::CMAX;
+            }
+            if (fits) break;
+            const int na = __popc(active & 0xffffu);
+            if (na < 2 || split >= 3 || nrows > 32u) {
+                slow |= active;
+                if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)na);
+                active = 0;
+                break;
+            }
+            // keep the lower half of the queries (cell-sorted: the lower half along x); the rest waits for a later pass
+            const unsigned keep = __ballot_sync(kFull, mine && __popc(active & ((1u << ql) - 1u)) < na / 2);
+            remaining |= active & ~keep;
+            active = keep;
+        }
+        if (!active) continue;
+
+        // ---- stage the region: one 1-D TMA bulk copy per row ------------------------------------
+        __syncwarp();
+        if (lane == 0) { ptx::fence_proxy_async_smem(); ptx::mbarrier_arrive_expect_tx(bar, C * 16u); }
+        __syncwarp();
+        if (len) ptx::bulk_g2s(stage + off, g.pts + s, len * 16u, bar);
+        if (C + (uint32_t)lane < C16) stage[C + lane] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
+        ptx::mbarrier_wait(bar, parity);
+        parity ^= 1u;
+        __syncwarp();
+
+        // ---- scan: the low lanes test the even staged slots, the high lanes the odd ones ------------
+        const float t2 = !mine ? -1.f : __fmul_rd(__fmul_rd(R, R), 0.9999f);
+        const float t2_safe = __fmul_rd(t2, 0.99999618530273f);
+        uint32_t* const wbase = list + lane;
+        const uint32_t waddr0 = ptx::smem_addr(wbase);
+        const uint32_t wclamp = waddr0 + (Cfg::LMAX + 1) * S * 4;
+        uint32_t waddr = waddr0;
+#define PGEOF_PAIR_APPEND(D2, SLOT)                                                           \
+        asm volatile("{\n\t.reg .pred p;\n\t"                                                 \
+                     "setp.le.f32 p, %1, %2;\n\t"                                             \
+                     "@p st.shared.u32 [%0], %3;\n\t"                                         \
+                     "@p add.u32 %0, %0, %4;\n\t}"                                            \
+                     : "+r"(waddr)                                                            \
+                     : "f"(D2), "f"(t2), "r"((__float_as_uint(D2) & ~Cfg::SLOT_MASK) | (SLOT)), "n"(S * 4));
+        for (uint32_t c = hi; c < C16; c += 16) {
+            float d[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 p = stage[c + 2 * i]; d[i] = sqdist_fused(qx, qy, qz, p.x, p.y, p.z); }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) PGEOF_PAIR_APPEND(d[i], c + 2 * i)
+            waddr = min(waddr, wclamp);
+        }
+#undef PGEOF_PAIR_APPEND
+        __syncwarp();
+        const uint32_t cnt_own = (waddr - waddr0) / (S * 4);
+        const uint32_t cnt_par = __shfl_xor_sync(kFull, cnt_own, 16);
+        const uint32_t cnt = cnt_own + cnt_par;                                   // survivors of the query
+        const bool over = cnt_own > (uint32_t)Cfg::LMAX || cnt_par > (uint32_t)Cfg::LMAX || cnt > 2u * NL;
+        bool ok = mine && cnt >= k && !over;
+        if (mine) *s_hint = R * (cnt < k ? fminf(cbrtf(1.25f * a.target / fmaxf((float)cnt, 2.f)), 3.f) : (over ? 0.88f : 1.f));
+        unsigned requeued = 0;
+        if (pass + 2 < Cfg::MAX_PASSES && !(a.flags & 2u)) {
+            const uint32_t retry = *s_retry;
+            const bool can = mine && (retry & 3u) < 2u;
+            const unsigned sh = __ballot_sync(kFull, can && cnt < k), ov = __ballot_sync(kFull, can && over);
+            if (__popc(sh & 0xffffu) >= Cfg::RETRY_MIN) {
+                if ((sh >> lane) & 1u) {
+                    *s_rmul *= fminf(fmaxf(exp2f(0.4f * log2f(1.3f * a.target / fmaxf((float)cnt, 1.f))), 1.15f), 3.f);
+                    *s_retry = ((retry & 3u) + 1u) | (1u << 2);
+                }
+                requeued |= sh;
+            }
+            if (__popc(ov & 0xffffu) >= Cfg::RETRY_MIN) {
+                if ((ov >> lane) & 1u) { *s_rmul *= 0.7f; *s_retry = ((retry & 3u) + 1u) | (2u << 2); }
+                requeued |= ov;
+            }
+            remaining |= requeued;
+        }
+        if (a.stats) {
+            const unsigned sh = __ballot_sync(kFull, mine && cnt < k), ov = __ballot_sync(kFull, mine && over);
+            const uint32_t sv = __reduce_add_sync(kFull, mine ? cnt_own : 0u);
+            if (lane == 0) {
+                atomicAdd(a.stats + ST_SHORT, (unsigned long long)__popc(sh & 0xffffu));
+                atomicAdd(a.stats + ST_OVER, (unsigned long long)__popc(ov & 0xffffu));
+                atomicAdd(a.stats + ST_PASSES, 1ull);
+                atomicAdd(a.stats + ST_CANDS, (unsigned long long)C);
+                atomicAdd(a.stats + ST_SURV, (unsigned long long)sv);
+            }
+        }
+
+        // ---- sort: NL keys per lane in registers -------------------------------------------------
+        uint32_t dropped;                      // smallest key outside the KOUT kept ranks (valid in both lanes after the shuffle)
+        uint32_t bad[HOUT / 32] = {};          // bit j: this lane's step j precedes its step j - 1 in the exact order
+        uint32_t fd = 0, fi = 0, ld = 0, li = 0;   // exact pair of this lane's first / last step
+        {
+            uint32_t v[NL];
+            // register i <- own entry i, or (own list exhausted) the partner's entry NL + (i - cnt_own)
+            const uint32_t own_a = waddr0;
+            const uint32_t par_a = ptx::smem_addr(list + (lane ^ 16)) + (uint32_t)((NL - (int)min(cnt_own, (uint32_t)NL)) * S * 4);
+            const uint32_t lim = min(cnt_own, (uint32_t)NL) + (cnt_par > (uint32_t)NL ? min(cnt_par, (uint32_t)Cfg::LMAX + 1u) - NL : 0u);
+#pragma unroll
+            for (int i = 0; i < NL; ++i) {
+                const uint32_t ad = ((uint32_t)i < cnt_own ? own_a : par_a) + (uint32_t)(i * S * 4);
+                uint32_t w;                    // predicated: an entry beyond `lim` may lie outside the list
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\tmov.u32 %0, %4;\n\t@p ld.shared.u32 %0, [%1];\n\t}"
+                             : "=r"(w) : "r"(ad), "r"((uint32_t)i), "r"(lim), "r"(Cfg::PAD));
+                v[i] = w ^ cm;
+            }
+            __syncwarp();                      // the lists are dead: their memory becomes the d2 plane
+            RegOddEvenSort<NL, 0, Cfg::VN>::run(v);
+            // low lane: the NL smallest of the pair's keys (complemented), high lane: the NL largest; both "down then up"
+#pragma unroll
+            for (int i = 0; i < NL; ++i) v[i] = max(v[i], ~__shfl_xor_sync(kFull, v[i], 16));
+            RegBitonicMerge<NL, 0, Cfg::VN>::run(v);
+            // low lane: v[i] = ~key of rank NL - 1 - i; high lane: v[i] = key of rank NL + i
+            if constexpr (KOUT < 2 * NL) dropped = __shfl_sync(kFull, v[KOUT - NL], ql + 16);      // rank KOUT lives in the high lane
+            else dropped = 0xffffffffu;
+            // ranks [HOUT, NL) move to the high lane; afterwards step j of either lane reads v[NL - 1 - j]
+            if (NX > 0) {
+#pragma unroll
+                for (int j = NX; j < HOUT; ++j) v[NL - 1 - j] = hi ? v[j - NX] : v[NL - 1 - j];
+#pragma unroll
+                for (int j = 0; j < NX; ++j) {          // low lane's rank HOUT + j (sources [0, NX) and targets [HOUT, NL) are disjoint)
+                    const uint32_t t = ~__shfl_xor_sync(kFull, v[NX - 1 - j], 16);
+                    v[NL - 1 - j] = hi ? t : v[NL - 1 - j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < HOUT / 2; ++j) {   // NL == HOUT: the high lane only reverses its registers
+                    const uint32_t x = v[j], y = v[NL - 1 - j];
+                    v[j] = hi ? y : x; v[NL - 1 - j] = hi ? x : y;
+                }
+            }
+            // rebuild the exact (d2, index) pairs: step j of this lane is rank hi * HOUT + j, plane[j * S + lane]
+            uint32_t* plane_d = list + lane;
+            uint32_t pd = 0, pi = 0;
+            const uint32_t rank0 = hi * HOUT;
+#pragma unroll
+            for (int j = 0; j < HOUT; ++j) {
+                const float4 p = stage[(v[NL - 1 - j] ^ cm) & Cfg::SLOT_MASK];
+                const uint32_t d = __float_as_uint(sqdist_f32(qx, qy, qz, p.x, p.y, p.z));
+                const uint32_t id = __float_as_uint(p.w);
+                if (j > 0) bad[j / 32] |= (rank0 + (uint32_t)j < cnt && (d < pd || (d == pd && id < pi))) ? (1u << (j % 32)) : 0u;
+                else { fd = d; fi = id; }
+                pd = d; pi = id;
+                plane_d[j * S] = d;
+                v[NL - 1 - j] = id;
+            }
+            ld = pd; li = pi;
+            __syncwarp();                      // the staged candidates are dead: index plane
+            uint32_t* plane_i = reinterpret_cast<uint32_t*>(stage) + lane;
+#pragma unroll
+            for (int j = 0; j < HOUT; ++j) plane_i[j * S] = v[NL - 1 - j];
+        }
+        {
+            // the high lane's first step follows the low lane's last one
+            const uint32_t qd = __shfl_xor_sync(kFull, ld, 16), qi = __shfl_xor_sync(kFull, li, 16);
+            if (hi && (uint32_t)HOUT < cnt && (fd < qd || (fd == qd && fi < qi))) bad[0] |= 1u;
+            uint32_t any_bad = 0;
+#pragma unroll
+            for (int r = 0; r < HOUT / 32; ++r) any_bad |= bad[r];
+            const uint32_t pair_bad = any_bad | __shfl_xor_sync(kFull, any_bad, 16);
+            __syncwarp();
+            uint32_t* const pd_q = list + ql;                                  // rank e of this query: [(e % HOUT) * S + (e / HOUT) * 16]
+            uint32_t* const pi_q = reinterpret_cast<uint32_t*>(stage) + ql;
+#define PGEOF_RANK_AT(e) (((e) % (uint32_t)HOUT) * S + ((e) / (uint32_t)HOUT) * 16u)
+            // the pair's inversion flags, by rank
+            uint32_t comb[MR];
+#pragma unroll
+            for (int r = 0; r < HOUT / 32; ++r) {
+                const uint32_t o = __shfl_xor_sync(kFull, bad[r], 16);
+                comb[r] = hi ? o : bad[r];
+                comb[r + HOUT / 32] = hi ? bad[r] : o;
+            }
+            if (ok && pair_bad && !hi) {
+                // insertion sort of the row on the exact (d2, index) order from the first inversion on (rare: truncated keys
+                // that collided); past the last inversion the first entry found in place ends it
+                uint32_t first = 0, last = 0;
+#pragma unroll
+                for (int r = MR - 1; r >= 0; --r) if (comb[r]) first = r * 32 + __ffs(comb[r]) - 1;
+#pragma unroll
+                for (int r = 0; r < MR; ++r) if (comb[r]) last = r * 32 + 31 - __clz(comb[r]);
+                const uint32_t nfix = min(cnt, (uint32_t)KOUT);
+                for (uint32_t i = first; i < nfix; ++i) {
+                    const uint32_t d = pd_q[PGEOF_RANK_AT(i)], id = pi_q[PGEOF_RANK_AT(i)];
+                    uint32_t j = i;
+                    while (j > 0) {
+                        const uint32_t qd2 = pd_q[PGEOF_RANK_AT(j - 1)], qi2 = pi_q[PGEOF_RANK_AT(j - 1)];
+                        if (qd2 < d || (qd2 == d && qi2 < id)) break;
+                        pd_q[PGEOF_RANK_AT(j)] = qd2; pi_q[PGEOF_RANK_AT(j)] = qi2;
+                        --j;
+                    }
+                    if (j != i) { pd_q[PGEOF_RANK_AT(j)] = d; pi_q[PGEOF_RANK_AT(j)] = id; }
+                    else if (i > last) break;
+                }
+            }
+            __syncwarp();
+            // exact iff (a) no dropped key can precede the k-th neighbour and (b) no rejected candidate can (see knn_tile_kernel)
+            const uint32_t kth = pd_q[PGEOF_RANK_AT(k - 1)];
+#undef PGEOF_RANK_AT
+            const bool tie = ok && ((dropped < Cfg::PAD && (dropped >> Cfg::SLOT_BITS) < (kth >> Cfg::SLOT_BITS) + 2u) ||
+                                    !(__uint_as_float(kth) <= t2_safe));
+            if (tie) ok = false;
+            if (a.stats) {
+                const unsigned tm = __ballot_sync(kFull, tie), fm = __ballot_sync(kFull, ok && pair_bad);
+                if (lane == 0) {
+                    atomicAdd(a.stats + ST_TIE, (unsigned long long)__popc(tm & 0xffffu));
+                    atomicAdd(a.stats + ST_FIXED, (unsigned long long)__popc(fm & 0xffffu));
+                }
+            }
+        }
+        slow |= __ballot_sync(kFull, mine && !ok) & ~requeued;
+        __syncwarp();
+        // ---- write the finished rows, one coalesced row at a time ---------------------------------
+        {
+            const uint32_t* plane_d = list;
+            const uint32_t* plane_i = reinterpret_cast<const uint32_t*>(stage);
+            const unsigned okm = __ballot_sync(kFull, ok);
+#pragma unroll 8
+            for (int q = 0; q < 16; ++q) {
+                const uint32_t rowq = __shfl_sync(kFull, row, q);
+                const size_t o = (size_t)rowq * k + lane;
+                uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + o;
+                float* d2 = a.sqr_dist + o;
+#pragma unroll
+                for (int r = 0; r < MR; ++r) {
+                    const uint32_t e = r * 32 + lane;
+                    const uint32_t at = (e % (uint32_t)HOUT) * S + (e / (uint32_t)HOUT) * 16u + (uint32_t)q;
+                    const uint32_t vi = plane_i[at], vd = plane_d[at];
+                    const uint32_t on = (((okm >> q) & 1u) && e < k) ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+                                 "@p st.global.u32 [%0], %2;\n\t@p st.global.u32 [%1], %3;\n\t}"
+                                 :: "l"(idx + r * 32), "l"(d2 + r * 32), "r"(vi), "r"(vd), "r"(on) : "memory");
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    if (slow & 0xffffu) {
+        const unsigned sl = slow & 0xffffu;
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(a.slow_count, (uint32_t)__popc(sl));
+        at = __shfl_sync(kFull, at, 0);
+        if ((sl >> lane) & 1u) a.slow_list[at + __popc(sl & lanemask_lt())] = make_uint2(base + lane, __float_as_uint(*s_hint));
+    }
+    if (unsafe & 0xffffu) {
+        const unsigned us = unsafe & 0xffffu;
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(a.unsafe_count, (uint32_t)__popc(us));
+        at = __shfl_sync(kFull, at, 0);
+        if ((us >> lane) & 1u) a.unsafe_list[at + __popc(us & lanemask_lt())] = make_uint2(base + lane, 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // any k: one CTA per query, keys in GLOBAL scratch (knn / max_knn beyond the 512 the register-resident select + sort of
 // search_kernel covers; the reference accepts any knn <= len(data), nn_search.hpp:37,92).  Same exactness argument
 // as the warp routine: the ball is grown until it holds k points, the 64-bit key threshold is bisected while more than
@@ -1019,12 +1442,12 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN, bool FUSED = false>
+template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN, bool FUSED = false, bool LOCK = true>
 int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
-    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE, FUSED>;
+    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE, FUSED, LOCK>;
     PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
     {
@@ -1038,12 +1461,30 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
+template <int NL, int HOUT, int NWARPS, int CMAX, int MINB>
+int launch_pair(const GridView& g, const SearchArgs& a, cudaStream_t stream)
+{
+    using Cfg = PairCfg<NL, HOUT, NWARPS, CMAX>;
+    const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
+    auto kern = knn_pair_kernel<NL, HOUT, NWARPS, CMAX, MINB>;
+    PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned blocks = (a.n_query + Cfg::WARPS * 16 - 1) / (Cfg::WARPS * 16);
+    {
+        KernelTimer timer("knn_search", stream);
+        kern<<<blocks, Cfg::WARPS * 32, smem, stream>>>(g, a);
+        knn_slow_kernel<Cfg::KOUT><<<sm_count() * 4, kWarps * 32, 0, stream>>>(g, a);
+    }
+    PGEOF_LAUNCH_CHECK();
+    PGEOF_LAUNCH_CHECK();
+    return PGEOF_OK;
+}
+
 // survivors the tile kernel's sorting network absorbs for a given k
 float env_float(const char* name, float dflt);
 
 // survivors the tile kernel's sorting network absorbs for a given k (a 128-key network for 52 < k <= 64 was
 // measured slower than this one at every k: 6 instead of 8 resident warps, 1342 instead of 985 comparators)
-inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : 96; }
+inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= 64 ? 96 : 192); }
 
 template <int MODE>
 int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, size_t n_data, cudaStream_t stream)
@@ -1077,7 +1518,10 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     if (n_query > 0xfffffff0ull) { set_error("n_query too large"); return PGEOF_EINVAL; }
     Grid grid;
     float target = 0.f;
-    const bool tile = (mode == SEARCH_KNN ? env_float("PGEOF_KNN_TILE", 1.f) != 0.f : mode == SEARCH_RADIUS && env_float("PGEOF_RADIUS_TILE", 1.f) != 0.f) && k <= 64;
+    // PGEOF_KNN_PAIR = 0 keeps the thread-per-query tile kernel for 32 < k <= 64 (and the warp-per-query routine above 64)
+    const bool pair = mode == SEARCH_KNN && k > 32 && k <= 128 && env_float("PGEOF_KNN_PAIR", 0.f) != 0.f;
+    const bool tile = (mode == SEARCH_KNN ? env_float("PGEOF_KNN_TILE", 1.f) != 0.f : mode == SEARCH_RADIUS && env_float("PGEOF_RADIUS_TILE", 1.f) != 0.f) &&
+                      (k <= 64 || pair);
     // the reference only ever uses r * r (nn_search.hpp:98): a negative radius searches the ball of |r|
     if (mode != SEARCH_KNN && !std::isfinite(radius)) { set_error("search_radius must be finite"); return PGEOF_EINVAL; }
     radius = std::fabs(radius);
@@ -1152,6 +1596,14 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         int st;
         if (mode == SEARCH_RADIUS) st = k <= 32 ? launch_tile<32, 32, 2, SEARCH_RADIUS>(grid.view, a, stream) : launch_tile<64, 32, 4, SEARCH_RADIUS>(grid.view, a, stream);
         else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
+        else if (pair && k <= 64) {
+            const int variant = (int)env_float("PGEOF_PAIR_VARIANT", 0.f);
+            st = variant == 1 ? launch_pair<48, 32, 3, 640, 3>(grid.view, a, stream)
+               : variant == 2 ? launch_pair<48, 32, 5, 640, 2>(grid.view, a, stream)
+                              : launch_pair<48, 32, 4, 512, 3>(grid.view, a, stream);
+        }
+        else if (pair) st = launch_pair<96, 64, 3, 896, 2>(grid.view, a, stream);
+        else if (env_float("PGEOF_KNN_LOCK", 1.f) == 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, false>(grid.view, a, stream);   // A/B switch
         else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
         uint32_t n_unsafe = 0;
         if (st == PGEOF_OK && clipped && mode == SEARCH_KNN) {
@@ -1164,7 +1616,8 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
                 b.slow_list = a.unsafe_list;
                 b.slow_count = a.unsafe_count;
                 if (k <= 32) knn_slow_kernel<32><<<sm_count() * 4, kWarps * 32, 0, stream>>>(full.view, b);
-                else knn_slow_kernel<64><<<sm_count() * 4, kWarps * 32, 0, stream>>>(full.view, b);
+                else if (k <= 64) knn_slow_kernel<64><<<sm_count() * 4, kWarps * 32, 0, stream>>>(full.view, b);
+                else knn_slow_kernel<128><<<sm_count() * 4, kWarps * 32, 0, stream>>>(full.view, b);
                 PGEOF_LAUNCH_CHECK();
             }
         }

@@ -240,9 +240,13 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&v)[M], int lane)
 template <int N>
 __device__ __forceinline__ void reg_cmpswap(uint32_t (&v)[N], int i, int j)
 {
-    const uint32_t a = v[i], b = v[j];
-    v[i] = min(a, b);
-    v[j] = max(a, b);
+    // a network laid over a VIRTUAL array longer than N (positions >= N hold +inf and never move: every comparator is
+    // (low index <- min, high index <- max)) is pruned to the comparators between real registers
+    if (i < N && j < N) {
+        const uint32_t a = v[i], b = v[j];
+        v[i] = min(a, b);
+        v[j] = max(a, b);
+    }
 }
 
 template <int N, int LO, int CNT, int R>
