@@ -65,7 +65,7 @@ struct MomentsD {
     }
     __device__ __forceinline__ void cov(uint32_t k, double (&c)[6]) const
     {
-        const double inv = 1.0 / (double)k;
+        const double inv = __drcp_rn((double)k);          // = 1.0 / k, correctly rounded, without the division's slow-path checks
         const double mx = sx * inv, my = sy * inv, mz = sz * inv;
         c[0] = sxx * inv - mx * mx; c[1] = sxy * inv - mx * my; c[2] = sxz * inv - mx * mz;
         c[3] = syy * inv - my * my; c[4] = syz * inv - my * mz; c[5] = szz * inv - mz * mz;
@@ -350,6 +350,168 @@ __global__ void __launch_bounds__(kRows, 4) optimal_direct_kernel(const FeatArgs
     for (int i = 0; i < 12; ++i) s_out[threadIdx.x * 12 + i] = f[i];
     store_rows<12>(a, t, s_out, s_rowid);
 }
+
+// ----------------------------------------------------------------------------------
+// compute_features_optimal, second version: one ROLLED scan loop per thread, cheap float filter.
+// The walker above inlines its accumulator at 22 sites, which forced the ~600-instruction evaluation out of line with its
+// state in local memory.  Here the offsets of 8 gathered neighbours go through shared memory ([slot][thread]: conflict
+// free) and one rolled loop consumes them, so the evaluation exists once, inline, with all state in registers:
+//   * prefix moments in double (as before: the covariance of every k is exact to ~1e-16 relative);
+//   * the FILTER entropy comes from float eigenvalues of a cyclic Jacobi iteration with approximate rotations
+//     (profiles/r2_summary.md: the IEEE divisions / square roots of the rotations were 68 % of the kernel's instructions);
+//   * a candidate within kOptMargin of the best is decided by the double closed-form entropies exactly as the all-double
+//     scan decides (strict '<', smallest k wins, pgeof.hpp:289): k_opt is identical.
+// ----------------------------------------------------------------------------------
+__device__ __noinline__ double entropy_f64_nv(double c0, double c1, double c2, double c3, double c4, double c5)
+{
+    const double c[6] = {c0, c1, c2, c3, c4, c5};
+    return entropy_f64(c);
+}
+
+// filter entropy in float with the fast log (|error| ~1e-7: three orders below kOptMargin)
+__device__ __forceinline__ float eigentropy_fast(float l0, float l1, float l2)
+{
+    const float eps = 1e-3f;
+    const float inv = __frcp_rn(l0 + l1 + l2 + eps);
+    const float e0 = l0 * inv, e1 = l1 * inv, e2 = l2 * inv;
+    return -0.69314718056f * (e0 * __log2f(e0 + eps) + e1 * __log2f(e1 + eps) + e2 * __log2f(e2 + eps));
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArgs a)
+{
+    __shared__ uint32_t s_rowid[kRows];
+    __shared__ __align__(128) float s_out[kRows * 12];     // source of a TMA bulk store: 16-B alignment required
+    __shared__ float s_d[24][kRows];                       // offsets of the 8 neighbours in flight: [3 u + axis][thread]
+    const uint32_t r0 = blockIdx.x * kRows;
+    Tile t{r0, min((uint32_t)kRows, a.n_rows - r0), a.order == nullptr};
+    float f[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) f[i] = 0.f;
+    uint32_t row = r0 + threadIdx.x;
+    if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
+    s_rowid[threadIdx.x] = row;
+    if (threadIdx.x < t.rows) {
+        unsigned long long b, e;
+        row_span(a, row, b, e);
+        if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);
+        else {
+            const uint32_t len = (uint32_t)(e - b);
+            const uint32_t* __restrict__ p = a.nn + b;
+            const bool eligible = len >= a.k_min && len >= a.k_min_search && len > 0;     // pgeof.hpp:272
+            const uint32_t i0 = eligible ? __ldg(p) : 0u;
+            bool ok = i0 < a.n_xyz;
+            if (eligible && !ok) atomicExch(a.err, 2);
+            if (eligible && ok) {
+                const uint32_t k0 = min(max(max(a.k_min, a.k_min_search), 1u), len);    // :274
+                const float4 o = __ldg(a.pts + i0);
+                MomentsD m;
+                double best_c[6] = {0, 0, 0, 0, 0, 0}, best_h64 = 0.0;
+                float best_h32 = 0.f;
+                uint32_t best_k = len;
+                bool have64 = false;
+                uint32_t rem = 0;                                                        // k % k_step, kept incrementally
+                float* const sd = &s_d[0][threadIdx.x];
+                uint32_t j = 0;
+                while (j < len) {
+                    // ---- next group of the nn stream: up to the next 32-byte boundary, then 8 at a time ----
+                    uint32_t i[8];
+                    const uint32_t lead = (uint32_t)(reinterpret_cast<uintptr_t>(p + j) & 31u) >> 2;
+                    uint32_t cnt;
+                    if (lead == 0 && j + 8 <= len) { stream_nn8(p + j, i); cnt = 8; }
+                    else {
+                        cnt = min(8u - lead, len - j);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) i[u] = (uint32_t)u < cnt ? __ldg(p + j + u) : i0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (i[u] >= a.n_xyz) { ok = false; i[u] = i0; }
+                    float4 q[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) q[u] = __ldg(a.pts + i[u]);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        sd[(3 * u + 0) * kRows] = q[u].x - o.x; sd[(3 * u + 1) * kRows] = q[u].y - o.y; sd[(3 * u + 2) * kRows] = q[u].z - o.z;
+                    }
+                    // ---- the scan proper: one rolled loop, the evaluation inline ----
+#pragma unroll 1
+                    for (uint32_t u = 0; u < cnt; ++u) {
+                        m.add((double)sd[(3 * u + 0) * kRows], (double)sd[(3 * u + 1) * kRows], (double)sd[(3 * u + 2) * kRows]);
+                        const uint32_t k = j + u + 1;
+                        rem = rem + 1 == a.k_step ? 0u : rem + 1;
+                        if (k < k0 || (k > k0 && rem != 0 && k != len)) continue;        // :283
+                        double c[6];
+                        m.cov(k, c);
+                        // float eigenvalues by cyclic Jacobi from the identity with APPROXIMATE rotations (MUFU reciprocal /
+                        // rsqrt: ~20 instructions per rotation instead of ~65 with IEEE division and square root).  A rotation
+                        // whose (c, s) is off by a few ulp is a similarity up to a factor 1 + O(1e-7): after <= 24 rotations the
+                        // diagonal holds the eigenvalues to ~3e-6 relative, most of it a COMMON scale error that cancels in the
+                        // ratios the entropy is made of; an off-diagonal left behind moves an eigenvalue by at most its size
+                        // (<= 1e-6 |C|).  |h32 - h64| <= ~5e-5, kOptMargin is 2e-4.
+                        float a00 = (float)c[0], a01 = (float)c[1], a02 = (float)c[2], a11 = (float)c[3], a12 = (float)c[4], a22 = (float)c[5];
+                        float scale = fmaxf(fmaxf(fabsf(a00), fabsf(a11)), fabsf(a22));
+                        scale = fmaxf(scale, fmaxf(fmaxf(fabsf(a01), fabsf(a02)), fabsf(a12)));
+                        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+                        if (scale > 0.f) {
+                            const float inv = __frcp_rn(scale);
+                            a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
+#define PGEOF_ROTF(app, aqq, apq, arp, arq)                                                   \
+                            if (fabsf(apq) > fmaxf(1e-9f * (fabsf(app) + fabsf(aqq)), 1e-18f)) {   \
+                                /* t = tan(phi) = sign(h apq) 2|apq| / (|h| + sqrt(h^2 + 4 apq^2)): three MUFU ops, no division */ \
+                                const float hh = aqq - app, t2a = 2.f * apq;                  \
+                                const float r1 = fmaf(hh, hh, t2a * t2a);                     \
+                                const float ta = fabsf(t2a) * __frcp_rn(fabsf(hh) + r1 * rsqrtf(r1)); \
+                                const float tt = __uint_as_float(__float_as_uint(ta) | ((__float_as_uint(hh) ^ __float_as_uint(apq)) & 0x80000000u)); \
+                                const float cs = rsqrtf(fmaf(tt, tt, 1.f)), sn = tt * cs;     \
+                                app = fmaf(-tt, apq, app); aqq = fmaf(tt, apq, aqq); apq = 0.f; \
+                                const float rp = arp, rq = arq;                               \
+                                arp = cs * rp - sn * rq; arq = sn * rp + cs * rq;             \
+                            } else apq = 0.f;
+#pragma unroll 1
+                            for (int sweep = 0; sweep < 8; ++sweep) {
+                                const float off = fabsf(a01) + fabsf(a02) + fabsf(a12);
+                                if (off <= 1e-6f * (fabsf(a00) + fabsf(a11) + fabsf(a22))) break;
+                                PGEOF_ROTF(a00, a11, a01, a02, a12)
+                                PGEOF_ROTF(a00, a22, a02, a01, a12)
+                                PGEOF_ROTF(a11, a22, a12, a01, a02)
+                            }
+#undef PGEOF_ROTF
+                            w0 = fmaxf(a00 * scale, 0.f); w1 = fmaxf(a11 * scale, 0.f); w2 = fmaxf(a22 * scale, 0.f);
+                        }
+                        const float h32 = eigentropy_fast(w0, w1, w2);
+                        bool take = k == k0 || h32 < best_h32 - kOptMargin;
+                        bool exact = false;
+                        double h64 = 0.0;
+                        if (!take && !(h32 > best_h32 + kOptMargin)) {                   // too close to call in float
+                            if (!have64) { best_h64 = entropy_f64_nv(best_c[0], best_c[1], best_c[2], best_c[3], best_c[4], best_c[5]); have64 = true; }
+                            h64 = entropy_f64_nv(c[0], c[1], c[2], c[3], c[4], c[5]);
+                            take = h64 < best_h64;                                       // pgeof.hpp:289
+                            exact = true;
+                        }
+                        if (take) {
+                            best_k = k; best_h32 = h32; best_h64 = h64; have64 = exact;
+#pragma unroll
+                            for (int z = 0; z < 6; ++z) best_c[z] = c[z];
+                        }
+                    }
+                    j += cnt;
+                }
+                if (!ok) atomicExch(a.err, 2);
+                else {
+                    float g[11];
+                    features11<float>(pca_from_cov<float>((float)best_c[0], (float)best_c[1], (float)best_c[2], (float)best_c[3],
+                                                         (float)best_c[4], (float)best_c[5], a.eig_order), g);
+#pragma unroll
+                    for (int z = 0; z < 11; ++z) f[z] = g[z];
+                    f[11] = (float)best_k;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s_out[threadIdx.x * 12 + i] = f[i];
+    store_rows<12>(a, t, s_out, s_rowid);
+}
 // ----------------------------------------------------------------------------------
 // pre-passes: Morton ordering of the cloud (float4 records + rank table) and of the rows
 // ----------------------------------------------------------------------------------
@@ -597,7 +759,13 @@ int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, siz
     PGEOF_TRY(prepare(&a, xyz, &pre, stream));
     {
         KernelTimer timer("optimal", stream);
-        optimal_direct_kernel<<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        // PGEOF_OPTIMAL_SCAN = 0: the first version (walker with the evaluation out of line), kept as an A/B switch
+        const int scan = env_int("PGEOF_OPTIMAL_SCAN", 1);
+        if (scan == 6) optimal_scan_kernel<6><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        else if (scan == 8) optimal_scan_kernel<8><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        else if (scan == 4) optimal_scan_kernel<4><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        else if (scan != 0) optimal_scan_kernel<5><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        else optimal_direct_kernel<<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
     }
     PGEOF_LAUNCH_CHECK();
     return device_flag_check(err.as<int>(), stream, "compute_features_optimal");
