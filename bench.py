@@ -406,7 +406,10 @@ def _main(real_stdout):
     dom_ms = kernels.get(dom, {"ms_per_step": float("nan")})["ms_per_step"]
     ach = alg[dom] / (dom_ms * 1e-3) / 1e9
     traffic, traffic_src = tracked_traffic()
-    per_row = traffic.get(cfg.get("traffic_key", args.config), {}).get(dom)
+    tcfg = traffic.get(cfg.get("traffic_key", args.config), {})
+    per_row = tcfg.get(dom)
+    if per_row and tcfg.get("_source"):
+        traffic_src = "%s <- %s" % (traffic_src, tcfg["_source"])
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": per_row * rows_dev if per_row else None, "traffic_source": traffic_src if per_row else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "kernel_ms_per_step": dom_ms,

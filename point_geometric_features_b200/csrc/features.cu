@@ -11,12 +11,13 @@
 // row's first neighbour), solves the 3x3 eigenproblem in registers (eig3.cuh) and the tile's features
 // leave through shared memory as 44-B row segments (permuted rows) or one TMA bulk store.
 //
-// What bounds it (profiles/r2_summary.md): not HBM.  Every gather of a warp instruction goes to a different 128-B
-// line (32 rows x their j-th neighbour), i.e. 32 L1 tag wavefronts per instruction: 5.6e8 wavefronts per 10 M x 50
-// launch = 2.0 ms at one wavefront per clock per SM; the kernel runs at ~73 % of that rate and its time does not move
-// when the DRAM traffic is changed by 60 % with L2 policies.  A Morton-sorted copy of the cloud behind a rank table
-// (rank[nn[j]] then the record) was built and measured in round 2: DRAM reads 6.1 -> 5.6 GB, but the table lookups
-// are as scattered as the gathers they replace -- same time, +0.3 ms of pre-pass -- and dropped.
+// What bounds it (profiles/r2_summary.md): not HBM.  The cloud is in input order, so every gathered point sits in its own
+// 128-B line: a 512-row CTA touches ~1950 distinct lines, two CTAs need 3900 L1 tags where ~1500 exist, 38 % of the 500 M
+// gathers of a 10 M x 50 launch miss L1 (3.8e8 L2 -> L1 sectors) and the kernel runs at the rate the SMs keep those misses in
+// flight (long_scoreboard: 17 stalled warps per issue); its time does not move when the DRAM traffic is changed by 60 % with
+// L2 policies.  A Morton-sorted copy of the cloud behind a rank table (rank[nn[j]] then the record) was built and measured in
+// round 2: DRAM reads 6.1 -> 5.6 GB, but a table lookup has the same one-line-per-lookup footprint as the gather it
+// replaces -- same time, +0.3 ms of pre-pass -- and was dropped.
 //
 // Algorithmic bytes per row of length k: 4k (nn) + 4 (nn_ptr) + 12k (xyz gather) + 44 (out)
 // = 48 + 16k.
@@ -761,10 +762,8 @@ int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, siz
         KernelTimer timer("optimal", stream);
         // PGEOF_OPTIMAL_SCAN = 0: the first version (walker with the evaluation out of line), kept as an A/B switch
         const int scan = env_int("PGEOF_OPTIMAL_SCAN", 1);
-        if (scan == 6) optimal_scan_kernel<6><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
-        else if (scan == 8) optimal_scan_kernel<8><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
-        else if (scan == 4) optimal_scan_kernel<4><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
-        else if (scan != 0) optimal_scan_kernel<5><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        // 6 CTAs of 128 rows per SM (80 registers): measured 26.8 / 23.4 / 22.5 / 23.0 ms per 10 M rows at 4 / 5 / 6 / 8
+        if (scan != 0) optimal_scan_kernel<6><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
         else optimal_direct_kernel<<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
     }
     PGEOF_LAUNCH_CHECK();

@@ -13,7 +13,7 @@ bench)
   timeout 600 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; cat $OUT/${TAG}_bench_n1.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('M', d['ms_per_step'], d['value'], d['roofline']['all_kernels'], d['e2e']['ms_per_step'] if d['e2e'] else None, d['cpu_baseline'])"
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err;;
 configs)
-  for c in C3 C4; do timeout 900 python bench.py --config $c --steps 5 --e2e-steps 2 > $OUT/${TAG}_bench_$c.json 2> $OUT/${TAG}_bench_$c.err; python -c "import sys,json; d=json.loads(open('$OUT/${TAG}_bench_$c.json').read()); print('$c', d['ms_per_step'], d['value'], d['roofline']['all_kernels'], d['e2e']['ms_per_step'] if d['e2e'] else None)"; done
+  for c in C2 C3 C4; do timeout 900 python bench.py --config $c --steps 5 --e2e-steps 2 > $OUT/${TAG}_bench_$c.json 2> $OUT/${TAG}_bench_$c.err; python -c "import sys,json; d=json.loads(open('$OUT/${TAG}_bench_$c.json').read()); print('$c', d['ms_per_step'], d['value'], d['roofline']['all_kernels'], d['e2e']['ms_per_step'] if d['e2e'] else None)"; done
   timeout 1200 python bench.py --config C5 --steps 3 --e2e-steps 1 > $OUT/${TAG}_bench_C5.json 2> $OUT/${TAG}_bench_C5.err; tail -c 600 $OUT/${TAG}_bench_C5.json; tail -3 $OUT/${TAG}_bench_C5.err;;
 ab)
   for v in "PGEOF_FEATURES_RANK=0" "PGEOF_FEATURES_CTA=256" "PGEOF_FEATURES_CTA=128"; do env $v timeout 300 python bench.py --steps 10 --no-e2e --no-cpu > $OUT/${TAG}_ab.json 2>/dev/null; python -c "import sys,json; d=json.loads(open('$OUT/${TAG}_ab.json').read()); print('$v', d['ms_per_step'], d['roofline']['all_kernels'])"; done;;
