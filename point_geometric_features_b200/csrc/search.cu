@@ -357,13 +357,20 @@ __device__ __forceinline__ uint32_t select_sort_network(uint32_t (&v)[NOUT + NEX
 // one instruction-cache fill serves all of them (profiles/r2_summary.md: the GPC-level instruction cache runs at 93 % of
 // its request rate when every warp streams the 62 KB of straight-line code on its own)
 #define PGEOF_LOCK_BARRIER() do { if (LOCK) asm volatile("bar.sync 0;" ::: "memory"); } while (0)
-template <int NOUT, int NEXTRA, int NWARPS, int MODE, bool FUSED = false, bool LOCK = false>
+// ROLLED: the exact rebuild is a rolled loop over sorted keys parked in shared memory and rows keep (d2, staged slot) pairs
+// (the index is read from the staged candidate when the row is written): 26 KB less straight-line code per pass and 128
+// instead of 255 registers, but the rolled loop has a quarter of the loads in flight: GCC requests 44 -> 33 M, kernel
+// 7.5 -> 8.2 ms (profiles/r2_summary.md).  Off by default; PGEOF_KNN_ROLLED=1 selects it for 32 < k <= 64.
+template <int NOUT, int NEXTRA, int NWARPS, int MODE, bool FUSED = false, bool LOCK = false, bool ROLLED = false>
 __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g, const SearchArgs a)
 {
     static_assert(MODE == SEARCH_KNN || MODE == SEARCH_RADIUS, "tile kernel: kNN or padded radius search");
     static_assert(!FUSED || MODE == SEARCH_KNN, "fused features: kNN only");
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     constexpr int M = NOUT / 32, NLOAD = Cfg::NLOAD, S = Cfg::STRIDE;
+    constexpr int PS = 34;                         // stride (in 16-bit entries) of the staged-slot plane: lane-private walks and column reads conflict free
+    constexpr bool SLOTS = FUSED || ROLLED;        // rows are (d2, staged slot) pairs until they are written
+    static_assert(NOUT * S * 4 + NOUT * PS * 2 <= Cfg::LIST_BYTES, "d2 plane + slot plane must fit in the list area");
     extern __shared__ __align__(128) unsigned char smem_tile[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem_tile + (size_t)warp * Cfg::SMEM_WARP_BYTES;
@@ -612,6 +619,29 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             // plane[i * S + lane] = i-th neighbour of this lane's row
             uint32_t* plane_d = list + lane;
             uint32_t pd = 0, pi = 0;
+            if (ROLLED) {
+                uint16_t* pslot = reinterpret_cast<uint16_t*>(list + NOUT * S) + lane;
+#pragma unroll
+                for (int i = 0; i < NOUT; ++i) plane_d[i * S] = v[i];       // sorted keys: the registers are free from here on
+#pragma unroll
+                for (int r = 0; r < M; ++r) {
+                    uint32_t b = 0;
+#pragma unroll 4
+                    for (int j = 0; j < 32; ++j) {
+                        const int i = r * 32 + j;
+                        const uint32_t slot = plane_d[i * S] & Cfg::SLOT_MASK;
+                        const float4 p = stage[slot];
+                        const uint32_t d = __float_as_uint(sqdist_f32(qx, qy, qz, p.x, p.y, p.z));
+                        const uint32_t id = __float_as_uint(p.w);
+                        b |= (i > 0 && (uint32_t)i < cnt && (d < pd || (d == pd && id < pi))) ? (1u << j) : 0u;
+                        pd = d; pi = id;
+                        if (MODE == SEARCH_RADIUS) nvalid += ((uint32_t)i < cnt && d < __float_as_uint(r2)) ? 1u : 0u;
+                        plane_d[i * S] = d;
+                        pslot[i * PS] = (uint16_t)slot;
+                    }
+                    bad[r] = b;
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < NOUT; ++i) {
                 const float4 p = stage[v[i] & Cfg::SLOT_MASK];
@@ -621,7 +651,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 pd = d; pi = id;
                 if (MODE == SEARCH_RADIUS) nvalid += ((uint32_t)i < cnt && d < __float_as_uint(r2)) ? 1u : 0u;
                 plane_d[i * S] = d;
-                if (FUSED) reinterpret_cast<uint16_t*>(list + NOUT * S)[i * 32 + lane] = (uint16_t)(v[i] & Cfg::SLOT_MASK);
+                if (FUSED) reinterpret_cast<uint16_t*>(list + NOUT * S)[i * PS + lane] = (uint16_t)(v[i] & Cfg::SLOT_MASK);
                 else v[i] = id;
             }
             if (!FUSED) {
@@ -630,6 +660,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 #pragma unroll
                 for (int i = 0; i < NOUT; ++i) plane_i[i * S] = v[i];
             }
+            }
         }
         {
             uint32_t* plane_d = list + lane;
@@ -637,7 +668,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             uint32_t any_bad = 0;
 #pragma unroll
             for (int r = 0; r < M; ++r) any_bad |= bad[r];
-            if (FUSED && ok && any_bad) {
+            if (SLOTS && ok && any_bad) {
                 // same repair on (d2, staged slot) pairs: the candidates stay staged, their index is read when two distances tie
                 uint16_t* pslot = reinterpret_cast<uint16_t*>(list + NOUT * S) + lane;
                 uint32_t first = 0, last = 0;
@@ -648,21 +679,21 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 const uint32_t nfix = min(cnt, (uint32_t)NOUT);
                 for (uint32_t i = first; i < nfix; ++i) {
                     const uint32_t d = plane_d[i * S];
-                    const uint16_t sl = pslot[i * 32];
+                    const uint16_t sl = pslot[i * PS];
                     const uint32_t id = __float_as_uint(stage[sl].w);
                     uint32_t j = i;
                     while (j > 0) {
                         const uint32_t qd = plane_d[(j - 1) * S];
-                        const uint16_t qs = pslot[(j - 1) * 32];
+                        const uint16_t qs = pslot[(j - 1) * PS];
                         if (qd < d || (qd == d && __float_as_uint(stage[qs].w) < id)) break;
-                        plane_d[j * S] = qd; pslot[j * 32] = qs;
+                        plane_d[j * S] = qd; pslot[j * PS] = qs;
                         --j;
                     }
-                    if (j != i) { plane_d[j * S] = d; pslot[j * 32] = sl; }
+                    if (j != i) { plane_d[j * S] = d; pslot[j * PS] = sl; }
                     else if (i > last) break;
                 }
             }
-            if (!FUSED && ok && any_bad) {
+            if (!SLOTS && ok && any_bad) {
                 // insertion sort on the exact (d2, index) order from the first inversion on; past the last
                 // inversion the first entry found in place ends it (everything behind it is in order already)
                 uint32_t first = 0, last = 0;
@@ -724,7 +755,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
                 Moments m;
 #pragma unroll 4
                 for (uint32_t i = 1; i < k; ++i) {
-                    const float4 p = stage[pslot[i * 32]];
+                    const float4 p = stage[pslot[i * PS]];
                     m.add(p.x - o.x, p.y - o.y, p.z - o.z);
                 }
                 features11<float>(m.pca(k, a.eig_order), f);
@@ -757,7 +788,9 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     const uint32_t e = r * 32 + lane;
-                    uint32_t vi = plane_i[e * S + q], vd = plane_d[e * S + q];
+                    uint32_t vi, vd = plane_d[e * S + q];
+                    if (SLOTS) vi = __float_as_uint(stage[reinterpret_cast<const uint16_t*>(list + NOUT * S)[e * PS + q]].w);
+                    else vi = plane_i[e * S + q];
                     if (MODE == SEARCH_RADIUS && e >= needq) { vi = 0xffffffffu; vd = 0u; }   // pad: -1 / 0 (nn_search.hpp:104,108)
                     const uint32_t on = (((okm >> q) & 1u) && e < k) ? 1u : 0u;
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
@@ -1442,12 +1475,12 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     return PGEOF_OK;
 }
 
-template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN, bool FUSED = false, bool LOCK = true>
+template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN, bool FUSED = false, bool LOCK = true, bool ROLLED = false>
 int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 {
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
-    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE, FUSED, LOCK>;
+    auto kern = knn_tile_kernel<NOUT, NEXTRA, NWARPS, MODE, FUSED, LOCK, ROLLED>;
     PGEOF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned blocks = (a.n_query + Cfg::WARPS * 32 - 1) / (Cfg::WARPS * 32);
     {
@@ -1603,7 +1636,8 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
                               : launch_pair<48, 32, 4, 512, 3>(grid.view, a, stream);
         }
         else if (pair) st = launch_pair<96, 64, 3, 896, 2>(grid.view, a, stream);
-        else if (env_float("PGEOF_KNN_LOCK", 1.f) == 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, false>(grid.view, a, stream);   // A/B switch
+        else if (env_float("PGEOF_KNN_ROLLED", 0.f) != 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, true, true>(grid.view, a, stream);   // A/B switches
+        else if (env_float("PGEOF_KNN_LOCK", 1.f) == 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, false>(grid.view, a, stream);
         else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
         uint32_t n_unsafe = 0;
         if (st == PGEOF_OK && clipped && mode == SEARCH_KNN) {

@@ -1,6 +1,13 @@
 #!/bin/bash
-OUT=gpurun_out; TAG=${1:-r2j}
-for v in 4 5 6 8; do
-  PGEOF_OPTIMAL_SCAN=$v timeout 600 python bench.py --config C5 --points 10000000 --steps 3 --no-e2e --no-cpu > $OUT/${TAG}_ab.json 2>/dev/null
-  python -c "import sys,json; d=json.loads(open('$OUT/${TAG}_ab.json').read()); print('$v C5@10M', 'step %.2f'%d['ms_per_step'], d['roofline']['all_kernels']['optimal'])"
+OUT=gpurun_out; TAG=${1:-r2l}
+mkdir -p $OUT
+timeout 900 python -m pytest tests -m gpu -q -x --timeout=600 -k "knn or upstream or metric or radius or fused or switch or clip or local or csr" > $OUT/${TAG}_pytest.log 2>&1; tail -3 $OUT/${TAG}_pytest.log
+for v in "PGEOF_KNN_ROLLED=1" "PGEOF_KNN_LOCK=0" "PGEOF_KNN_ROLLED=0"; do
+  env $v timeout 300 python bench.py --steps 8 --no-e2e --no-cpu > $OUT/${TAG}_ab.json 2>/dev/null
+  python -c "import sys,json; d=json.loads(open('$OUT/${TAG}_ab.json').read()); print('$v', 'step %.2f'%d['ms_per_step'], 'knn %.2f'%d['roofline']['all_kernels']['knn_search']['ms'])"
+  env $v timeout 300 ncu --metrics gcc__cache_requests_type_instruction.sum,gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed,sm__icc_request_hit_rate.pct,smsp__issue_active.avg.per_cycle_active,gpu__time_duration.sum,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__inst_executed.sum --clock-control none -k regex:knn_tile -s 3 -c 1 --csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep -E "knn_tile" | awk -F'","' '{print "    ", $(NF-2), $(NF)}'
 done
+timeout 300 python bench.py --config C3 --steps 5 --no-e2e --no-cpu > $OUT/${TAG}_ab.json 2>/dev/null
+python -c "import sys,json; d=json.loads(open('$OUT/${TAG}_ab.json').read()); print('C3', 'step %.2f'%d['ms_per_step'], d['roofline']['all_kernels'])"
+python tools/fused_probe.py 2>&1 | tail -2
+timeout 300 python tools/fuzz_search.py 120 2>&1 | tail -2
