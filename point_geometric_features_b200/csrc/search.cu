@@ -309,8 +309,9 @@ struct TileCfg {
     static constexpr int LCAP = NLOAD + 1 + SINK;  // list entries per lane
     static constexpr int STRIDE = 33;              // entry stride in words: lane-private walks AND column reads are conflict free
     static constexpr int WARPS = NWARPS;
-    static constexpr int CMAX = 872;               // candidates staged per pass (16 B each), multiple of 8
-    static constexpr int LIST_BYTES = LCAP * STRIDE * 4;
+    static constexpr int CMAX = NOUT > 64 ? 1016 : 872;   // candidates staged per pass (16 B each), multiple of 8
+    static constexpr int PLANE_BYTES = NOUT * STRIDE * 4 + NOUT * 34 * 2;   // rolled rebuild: d2 plane + 16-bit staged-slot plane
+    static constexpr int LIST_BYTES = ((LCAP * STRIDE * 4 > PLANE_BYTES ? LCAP * STRIDE * 4 : PLANE_BYTES) + 15) / 16 * 16;
     static constexpr int STAGE_BYTES = CMAX * 16;
     static constexpr int BAR_BYTES = 16 + 3 * 128;   // mbarrier + three per-lane words kept out of the register file (see below)
     static constexpr int SMEM_WARP_BYTES = STAGE_BYTES + LIST_BYTES + BAR_BYTES;
@@ -324,7 +325,7 @@ struct TileCfg {
     static constexpr uint32_t PAD = ~SLOT_MASK;    // key of an empty list position: above every real key (d2 bits of a NaN), slot 0
     static_assert(CMAX % 8 == 0 && CMAX <= (1 << SLOT_BITS), "slot field too small");
     static_assert(LIST_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "alignment");
-    static_assert(NOUT * STRIDE * 4 <= LIST_BYTES && NOUT * STRIDE * 4 <= STAGE_BYTES, "output planes must fit");
+    static_assert(NOUT * STRIDE * 4 <= LIST_BYTES && (NOUT > 64 || NOUT * STRIDE * 4 <= STAGE_BYTES), "output planes must fit (NOUT > 64: rolled rebuild only, no index plane)");
     static_assert((1 << SLOT_BITS) * 16 <= SMEM_WARP_BYTES, "a padded slot must stay inside the warp's shared memory");
     static_assert(NOUT % 32 == 0 && NEXTRA % 32 == 0 && NEXTRA <= NOUT, "network shape");
 };
@@ -1517,7 +1518,7 @@ float env_float(const char* name, float dflt);
 
 // survivors the tile kernel's sorting network absorbs for a given k (a 128-key network for 52 < k <= 64 was
 // measured slower than this one at every k: 6 instead of 8 resident warps, 1342 instead of 985 comparators)
-inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= 64 ? 96 : 192); }
+inline int tile_nload(uint32_t k) { return k <= 32 ? 64 : (k <= 64 ? 96 : 160); }
 
 template <int MODE>
 int dispatch_search(uint32_t k, const GridView& g, const SearchArgs& a, size_t n_data, cudaStream_t stream)
@@ -1552,9 +1553,13 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
     Grid grid;
     float target = 0.f;
     // PGEOF_KNN_PAIR = 0 keeps the thread-per-query tile kernel for 32 < k <= 64 (and the warp-per-query routine above 64)
-    const bool pair = mode == SEARCH_KNN && k > 32 && k <= 128 && env_float("PGEOF_KNN_PAIR", 0.f) != 0.f;
+    const bool pair = mode == SEARCH_KNN && k > 32 && k <= 64 && env_float("PGEOF_KNN_PAIR", 0.f) != 0.f;
+    // 64 < k <= 128: PGEOF_KNN_TILE128 = 1 runs the tile kernel with a 160-key network and the rolled rebuild (254 registers,
+    // 42 KB of shared memory per warp -> 5 warps per SM).  Bit-exact, measured at 10 M x k = 100: 31.4 ms against 25.0 ms
+    // for the warp-per-query routine (887 candidates per pass, 20 % of the rows need the tie repair) -> off by default.
+    const bool tile128 = mode == SEARCH_KNN && k > 64 && k <= 128 && env_float("PGEOF_KNN_TILE128", 0.f) != 0.f;
     const bool tile = (mode == SEARCH_KNN ? env_float("PGEOF_KNN_TILE", 1.f) != 0.f : mode == SEARCH_RADIUS && env_float("PGEOF_RADIUS_TILE", 1.f) != 0.f) &&
-                      (k <= 64 || pair);
+                      (k <= 64 || tile128);
     // the reference only ever uses r * r (nn_search.hpp:98): a negative radius searches the ball of |r|
     if (mode != SEARCH_KNN && !std::isfinite(radius)) { set_error("search_radius must be finite"); return PGEOF_EINVAL; }
     radius = std::fabs(radius);
@@ -1635,7 +1640,7 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
                : variant == 2 ? launch_pair<48, 32, 5, 640, 2>(grid.view, a, stream)
                               : launch_pair<48, 32, 4, 512, 3>(grid.view, a, stream);
         }
-        else if (pair) st = launch_pair<96, 64, 3, 896, 2>(grid.view, a, stream);
+        else if (k > 64) st = launch_tile<128, 32, 5, SEARCH_KNN, false, true, true>(grid.view, a, stream);
         else if (env_float("PGEOF_KNN_ROLLED", 0.f) != 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, true, true>(grid.view, a, stream);   // A/B switches
         else if (env_float("PGEOF_KNN_LOCK", 1.f) == 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, false>(grid.view, a, stream);
         else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);

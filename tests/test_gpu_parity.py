@@ -598,7 +598,7 @@ def test_optimal_k_against_the_float32_arithmetic_of_the_reference():
         assert (margin32[differ] < 1e-5).all()
 
 
-SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"),
+SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"), ("PGEOF_KNN_TILE128", "1"),
             ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0")]
 
 
@@ -615,13 +615,14 @@ def test_every_switch_leaves_the_results_unchanged(name, value, monkeypatch):
             monkeypatch.setenv(name, value)
         idx, d2 = pgeof.knn_search(t, t, 50)
         qi, qd = pgeof.knn_search(t, q, 20)
+        wi, wd = pgeof.knn_search(t, t[:30000], 100)                                 # 64 < k <= 128 (PGEOF_KNN_TILE128)
         ri, rd = pgeof.radius_search(t, t, 6.0, 40)
         ptr = (torch.arange(len(xyz) + 1, device="cuda") * 50).to(torch.uint32)
         f = pgeof.compute_features(t, idx.view(-1), ptr)
         ms = pgeof.compute_features_multiscale(t, idx.view(-1), ptr, [10, 50])
         op = pgeof.compute_features_optimal(t, idx.view(-1), ptr, 1, 1, 10)
         fu = b200.knn_features(t, 50)
-        got = [x.cpu().numpy().view(np.uint32) for x in (idx, d2, qi, qd, ri, rd, f, ms, op, fu)]
+        got = [x.cpu().numpy().view(np.uint32) for x in (idx, d2, qi, qd, wi, wd, ri, rd, f, ms, op, fu)]
         if phase == "default":
             base = got
             ref = cpu.knn_search(xyz, xyz[:3000], 50)
