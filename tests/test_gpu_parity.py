@@ -550,6 +550,109 @@ def test_metric_workload_full_size_properties():
     assert bool(torch.isfinite(feats).all())
 
 
+def _recomputed_d2(t, q, idx64):
+    """the defined float32 metric fl(fl(dx^2 + dy^2) + dz^2) of the returned indices, on the device"""
+    diff = q[:, None, :] - t[idx64]
+    return (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
+
+
+def test_c3_full_size_radius_csr_features():
+    """BASELINE config 3 at its stated size: 10 M LiDAR-like points, radius_search r = 0.2, max_k = 64 -> CSR ->
+    compute_features.  Size-independent properties on every row + sampled rows against the oracle over the full cloud."""
+    import torch
+    n, r, mk = 10_000_000, 0.2, 64
+    xyz = synth.lidar_like_cloud(n, seed=0)
+    t = torch.from_numpy(xyz).cuda()
+    ridx, rd2 = pgeof.radius_search(t, t, r, mk)
+    nn, nn_ptr = b200.radius_search_csr(t, t, r, mk)
+    feats = pgeof.compute_features(t, nn, nn_ptr)
+    torch.cuda.synchronize()
+    valid = ridx >= 0
+    cnt = valid.sum(1)
+    # padding is a suffix of -1 / 0, kept entries are strictly inside the ball and sorted, the query itself comes first
+    assert bool((valid[:, 1:] <= valid[:, :-1]).all()) and bool((rd2[~valid] == 0).all())
+    r2 = float(np.float32(r) * np.float32(r))
+    assert bool((rd2[valid] < r2).all())
+    big = torch.where(valid, rd2, torch.full_like(rd2, 3e38))
+    assert bool((big[:, 1:] >= big[:, :-1]).all())
+    assert bool((rd2[:, 0] == 0).all()) and int(cnt.min()) >= 1
+    # the CSR entry point emits exactly the compacted table
+    ptr64 = nn_ptr.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    assert bool((ptr64[1:] - ptr64[:-1] == cnt).all()) and int(ptr64[-1]) == nn.shape[0]
+    assert bool((nn.view(torch.int32) == ridx[valid]).all())
+    # sampled rows: distances recomputed on the device, rows and features against the oracle over the full cloud
+    sample = np.sort(np.random.default_rng(5).choice(n, 2000, replace=False))
+    sd = torch.from_numpy(sample).cuda()
+    re = _recomputed_d2(t, t[sd], ridx[sd].clamp(min=0).to(torch.int64))
+    assert bool((re[valid[sd]] == rd2[sd][valid[sd]]).all())
+    ref = cpu.radius_search(xyz, xyz[sample], r, mk)
+    _assert_search_equal((ridx[sd].cpu().numpy(), rd2[sd].cpu().numpy()), ref)
+    rnn, rptr = radius_csr(ref[0])
+    fref = cpu.compute_features(xyz, rnn, rptr)
+    compare_features(feats[sd].cpu().numpy(), fref, row_eigvals(xyz, rnn, rptr), "literal", "C3 features", **LIDAR)
+    assert bool(torch.isfinite(feats).all())
+
+
+def test_c4_full_size_knn100_multiscale():
+    """BASELINE config 4 at its stated size: 10 M uniform points, one k = 100 kNN pass, k_scales = [10, 20, 50, 100]."""
+    import torch
+    n, k, scales = 10_000_000, 100, [10, 20, 50, 100]
+    xyz = synth.uniform_cloud(n, seed=0)
+    t = torch.from_numpy(xyz).cuda()
+    idx, d2 = pgeof.knn_search(t, t, k)
+    nn_ptr = (torch.arange(n + 1, device="cuda", dtype=torch.int64) * k).to(torch.uint32)
+    ms = pgeof.compute_features_multiscale(t, idx.view(-1), nn_ptr, scales)
+    torch.cuda.synchronize()
+    assert tuple(ms.shape) == (n, 4, 11) and bool(torch.isfinite(ms).all())
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    idx64 = idx.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    assert bool((idx64[:, 0] == torch.arange(n, device="cuda")).all()) and int(idx64.max()) < n
+    rows = torch.from_numpy(np.random.default_rng(3).choice(n, 100000, replace=False)).cuda()
+    assert bool((_recomputed_d2(t, t[rows], idx64[rows]) == d2[rows]).all())
+    sample = np.random.default_rng(4).choice(n, 256, replace=False)
+    ref = cpu.knn_search(xyz, xyz[sample], k, brute=True)
+    sd = torch.from_numpy(sample).cuda()
+    _assert_search_equal((idx64[sd].cpu().numpy().astype(np.uint32), d2[sd].cpu().numpy()), ref)
+    fref = cpu.compute_features_multiscale(xyz, ref[0].reshape(-1), (np.arange(257) * k).astype(np.uint32), scales)
+    got = ms[sd].cpu().numpy()
+    for s_, ks in enumerate(scales):
+        compare_features(got[:, s_], fref[:, s_], row_eigvals_dense(xyz, ref[0][:, :ks]), "literal", "C4 scale %d" % ks, **UNIFORM)
+
+
+def test_c5_full_size_shard_knn100_optimal():
+    """BASELINE config 5 at its stated size: a 50 M-point cloud, one rank's slab of the query-sharded run (1 / 25 of the
+    rows, shard-local CSR offsets as pgeof.hpp:83 allows), kNN k = 100 -> compute_features_optimal(k_min_search = 10)."""
+    import torch
+    from point_geometric_features_b200 import shard
+    n, k = 50_000_000, 100
+    xyz = synth.uniform_cloud(n, seed=0)
+    t = torch.from_numpy(xyz).cuda()
+    rows, q = shard.slab_queries(t, 7, 25)
+    m = int(q.shape[0])
+    assert abs(m - n // 25) < n // 250
+    idx, d2 = pgeof.knn_search(t, q, k)
+    nn_ptr = (torch.arange(m + 1, device="cuda", dtype=torch.int64) * k).to(torch.uint32)
+    opt = pgeof.compute_features_optimal(t, idx.view(-1), nn_ptr, 1, 1, 10)
+    torch.cuda.synchronize()
+    assert tuple(opt.shape) == (m, 12) and bool(torch.isfinite(opt).all())
+    assert bool((opt[:, 11] >= 10).all()) and bool((opt[:, 11] <= k).all())
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    idx64 = idx.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    assert bool((idx64[:, 0] == rows).all())
+    pick = np.random.default_rng(8).choice(m, 96, replace=False)
+    pd_ = torch.from_numpy(pick).cuda()
+    qs = q[pd_].cpu().numpy()
+    ref = cpu.knn_search(xyz, qs, k, brute=True)
+    _assert_search_equal((idx64[pd_].cpu().numpy().astype(np.uint32), d2[pd_].cpu().numpy()), ref)
+    fref, margin = cpu.compute_features_optimal(xyz, ref[0].reshape(-1), (np.arange(97) * k).astype(np.uint32), 1, 1, 10, return_margin=True)
+    got = opt[pd_].cpu().numpy()
+    sure = margin > 1e-9
+    np.testing.assert_array_equal(got[sure, 11], fref[sure, 11])
+    kopt = fref[:, 11].astype(int)
+    ev = np.stack([np.linalg.eigvalsh(np.cov(xyz[ref[0][i, :kk]].astype(np.float64).T, bias=True)) for i, kk in enumerate(kopt)])
+    compare_features(got[sure, :11], fref[sure, :11], ev[sure], "literal", "C5 optimal features", max_weak=0.05, max_degenerate=0.0, max_ill=0.02)
+
+
 # --------------------------------------------------------------------------------------------
 # round 2: any k, |r|, the reference's float32 optimal-k arithmetic, every PGEOF_* switch, fused path vs the oracle
 # --------------------------------------------------------------------------------------------
