@@ -181,6 +181,7 @@ void DeviceBuffer::release()
 struct HostCtx {
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy = nullptr;      // second stream of the chunked host pipelines (uploads run beside compute + downloads)
 };
 static thread_local HostCtx g_ctx;
 
@@ -204,8 +205,13 @@ static int host_stream(cudaStream_t* s)
     int dev = 0;
     PGEOF_TRY(ensure_device(&dev));
     if (g_ctx.device != dev || !g_ctx.stream) {
-        if (g_ctx.stream) { cudaSetDevice(g_ctx.device); cudaStreamDestroy(g_ctx.stream); cudaSetDevice(dev); g_ctx.stream = nullptr; }
+        if (g_ctx.stream) {
+            cudaSetDevice(g_ctx.device); cudaStreamDestroy(g_ctx.stream);
+            if (g_ctx.copy) cudaStreamDestroy(g_ctx.copy);
+            cudaSetDevice(dev); g_ctx.stream = nullptr; g_ctx.copy = nullptr;
+        }
         PGEOF_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        PGEOF_CUDA(cudaStreamCreateWithFlags(&g_ctx.copy, cudaStreamNonBlocking));
         g_ctx.device = dev;
     }
     *s = g_ctx.stream;
@@ -789,6 +795,86 @@ struct CsrOnDevice {
     }
 };
 
+}  // extern "C" (templates need C++ linkage)
+
+// Chunked host pipeline of the CSR feature functions.  The serial flavour uploads all of nn (2 GB at 10 M x 50), computes,
+// downloads; here the rows are cut into up to 16 chunks whose nn slices go up on a copy stream into two alternating buffers
+// while the previous chunk is computed and its rows go down on the compute stream: both PCIe directions and the SMs are
+// busy at once, and the device holds two slices instead of the whole list.  run(nn, nnz_end, row offsets, rows, out)
+// sees a pointer `slice - lo`, so the caller's absolute offsets address the slice; rows that point outside [lo, nnz_end)
+// (a corrupt, non-monotonic nn_ptr) are refused by the kernels (FeatArgs::nn_lo) exactly like offsets beyond nnz.
+// Returns 1 in *done when the pipeline ran, 0 when the input is too small or its chunk boundaries are not monotonic
+// (the serial flavour then reports the error).
+struct EventPair {
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int create() { for (auto& e : ev) PGEOF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return PGEOF_OK; }
+    ~EventPair() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
+
+template <typename Run>
+static int csr_pipeline(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const void* nn_ptr, int ptr_bytes, size_t n_rows,
+                        size_t floats_per_row, float* out, cudaStream_t s, Run run, int* done)
+{
+    *done = 0;
+    const char* env = std::getenv("PGEOF_HOST_CHUNK_MB");
+    const size_t chunk_bytes = (size_t)(env ? std::max(1, std::atoi(env)) : 128) << 20;
+    if (env && std::atoi(env) <= 0) return PGEOF_OK;                                     // PGEOF_HOST_CHUNK_MB=0: serial flavour
+    const size_t chunks = std::min(std::min((nnz * 4 + chunk_bytes - 1) / chunk_bytes, (size_t)16), n_rows);
+    if (chunks < 2 || !nn) return PGEOF_OK;
+    auto off = [&](size_t r) -> unsigned long long {
+        return ptr_bytes == 8 ? reinterpret_cast<const unsigned long long*>(nn_ptr)[r] : reinterpret_cast<const uint32_t*>(nn_ptr)[r];
+    };
+    const size_t per = (n_rows + chunks - 1) / chunks;
+    unsigned long long max_len = 0, prev = off(0);
+    for (size_t c = 0; c < chunks; ++c) {
+        const unsigned long long hi = off(std::min(n_rows, (c + 1) * per));
+        if (hi < prev || hi > nnz) return PGEOF_OK;
+        max_len = std::max(max_len, hi - prev);
+        prev = hi;
+    }
+    cudaStream_t up = g_ctx.copy;
+    DeviceBuffer d_xyz, d_ptr, d_out, d_nn[2];
+    PGEOF_TRY(h2d(&d_xyz, xyz, n_xyz * 12, s));
+    PGEOF_TRY(h2d(&d_ptr, nn_ptr, (n_rows + 1) * (size_t)ptr_bytes, s));
+    PGEOF_TRY(d_out.alloc(n_rows * floats_per_row * 4, s));
+    for (auto& b : d_nn) PGEOF_TRY(b.alloc(std::max<size_t>((size_t)max_len * 4, 16), s));
+    EventPair uploaded, consumed, ready;
+    PGEOF_TRY(uploaded.create()); PGEOF_TRY(consumed.create()); PGEOF_TRY(ready.create());
+    PGEOF_CUDA(cudaEventRecord(ready.ev[0], s));                                         // the buffers exist (arena blocks are stream ordered)
+    PGEOF_CUDA(cudaStreamWaitEvent(up, ready.ev[0], 0));
+    auto upload = [&](size_t c) -> int {
+        const size_t r0 = c * per, r1 = std::min(n_rows, (c + 1) * per);
+        const unsigned long long lo = off(r0), hi = off(r1);
+        if (c >= 2) PGEOF_CUDA(cudaStreamWaitEvent(up, consumed.ev[c & 1], 0));
+        if (hi > lo) PGEOF_CUDA(cudaMemcpyAsync(d_nn[c & 1].ptr, nn + lo, (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, up));
+        PGEOF_CUDA(cudaEventRecord(uploaded.ev[c & 1], up));
+        return PGEOF_OK;
+    };
+    PGEOF_TRY(upload(0));
+    int status = PGEOF_OK;
+    for (size_t c = 0; c < chunks && status == PGEOF_OK; ++c) {
+        const size_t r0 = c * per, r1 = std::min(n_rows, (c + 1) * per);
+        if (r1 <= r0) break;
+        if (c + 1 < chunks) PGEOF_TRY(upload(c + 1));
+        const unsigned long long lo = off(r0), hi = off(r1);
+        PGEOF_CUDA(cudaStreamWaitEvent(s, uploaded.ev[c & 1], 0));
+        g_nn_window_lo = lo;
+        const RowPtr rows_ptr = ptr_bytes == 8 ? RowPtr(d_ptr.as<unsigned long long>() + r0) : RowPtr(d_ptr.as<uint32_t>() + r0);
+        status = run(d_xyz.as<float>(), d_nn[c & 1].as<uint32_t>() - lo, (size_t)hi, rows_ptr, r1 - r0, d_out.as<float>() + r0 * floats_per_row);
+        g_nn_window_lo = 0;
+        PGEOF_CUDA(cudaEventRecord(consumed.ev[c & 1], s));
+        if (status == PGEOF_OK)
+            PGEOF_CUDA(cudaMemcpyAsync(out + r0 * floats_per_row, d_out.as<float>() + r0 * floats_per_row, (r1 - r0) * floats_per_row * 4, cudaMemcpyDeviceToHost, s));
+    }
+    PGEOF_CUDA(cudaStreamSynchronize(up));
+    PGEOF_CUDA(cudaStreamSynchronize(s));
+    if (status != PGEOF_OK) return status;
+    *done = 1;
+    return PGEOF_OK;
+}
+
+extern "C" {
+
 static int features_host_core(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz, const void* nn_ptr, int ptr_bytes, size_t n_rows,
                               uint32_t k_min, int eig_order, float* out)
 {
@@ -798,6 +884,12 @@ static int features_host_core(const float* xyz, size_t n_xyz, const uint32_t* nn
     if (n_rows == 0) return PGEOF_OK;
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
     HostTrace trace("compute_features", s);
+    int piped = 0;
+    PGEOF_TRY(csr_pipeline(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, 11, out, s,
+                           [&](const float* dx, const uint32_t* dnn, size_t end, RowPtr rp, size_t rows, float* dout) {
+                               return features_run(dx, n_xyz, dnn, end, rp, rows, k_min, eig_order, dout, s);
+                           }, &piped));
+    if (piped) { trace.mark("chunked h2d | features | d2h"); return PGEOF_OK; }
     CsrOnDevice d;
     PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_rows * 11, s));
     trace.mark("alloc+h2d");
@@ -818,6 +910,12 @@ static int multiscale_host_core(const float* xyz, size_t n_xyz, const uint32_t* 
     PGEOF_TRY(host_stream(&s));
     if (n_rows == 0 || n_scales == 0) return PGEOF_OK;
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    int piped = 0;
+    PGEOF_TRY(csr_pipeline(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_scales * 11, out, s,
+                           [&](const float* dx, const uint32_t* dnn, size_t end, RowPtr rp, size_t rows, float* dout) {
+                               return features_multiscale_run(dx, n_xyz, dnn, end, rp, rows, k_scales, n_scales, eig_order, dout, s);
+                           }, &piped));
+    if (piped) return PGEOF_OK;
     CsrOnDevice d;
     PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_rows * n_scales * 11, s));
     PGEOF_TRY(features_multiscale_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.dptr, n_rows, k_scales, n_scales,
@@ -836,6 +934,12 @@ static int optimal_host_core(const float* xyz, size_t n_xyz, const uint32_t* nn,
     PGEOF_TRY(host_stream(&s));
     if (n_rows == 0) return PGEOF_OK;
     PGEOF_REQUIRE(xyz && nn_ptr && out && (nn || nnz == 0), "null pointer argument");
+    int piped = 0;
+    PGEOF_TRY(csr_pipeline(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, 12, out, s,
+                           [&](const float* dx, const uint32_t* dnn, size_t end, RowPtr rp, size_t rows, float* dout) {
+                               return features_optimal_run(dx, n_xyz, dnn, end, rp, rows, k_min, k_step, k_min_search, eig_order, dout, s);
+                           }, &piped));
+    if (piped) return PGEOF_OK;
     CsrOnDevice d;
     PGEOF_TRY(d.stage(xyz, n_xyz, nn, nnz, nn_ptr, ptr_bytes, n_rows, n_rows * 12, s));
     PGEOF_TRY(features_optimal_run(d.xyz.as<float>(), n_xyz, d.nn.as<uint32_t>(), nnz, d.dptr, n_rows, k_min, k_step,

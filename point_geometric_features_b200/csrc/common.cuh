@@ -150,6 +150,10 @@ int selected_run_f32(const float* xyz, size_t n, float radius, uint32_t max_knn,
 int selected_run_f64(const double* xyz, size_t n, double radius, uint32_t max_knn, const int32_t* ids_host, size_t n_ids,
                      int eig_order, double* out, cudaStream_t stream);
 
+// Window of the caller's nn array that is resident behind the `nn` pointer of the next feature call of this thread: rows may
+// only address nn[lo, nnz).  Used by the chunked host pipeline, which passes `slice - lo` as nn; 0 otherwise.
+extern thread_local unsigned long long g_nn_window_lo;
+
 // per-block bounding boxes of an (n,3) cloud: out[b*6 + {0..2}] = min, out[b*6 + {3..5}] = max
 int bbox_partials(const float* xyz, size_t n, DeviceBuffer* out, int* n_partials, cudaStream_t stream);
 

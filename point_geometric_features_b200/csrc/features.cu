@@ -42,6 +42,7 @@ struct FeatArgs {
     const float4* pts;            // the cloud as 16-B float4 records (input order): one LDG.128 per gather
     const uint32_t* order;        // spatial row permutation, or nullptr = identity
     const uint32_t* nn; unsigned long long nnz;
+    unsigned long long nn_lo;              // rows may only address nn[nn_lo, nnz): a host pipeline hands the kernels one slice of nn at a time
     const uint32_t* nn_ptr;                // row offsets, uint32 (the reference's dtype) ...
     const unsigned long long* nn_ptr64;    // ... or uint64 (extension: more than 2^32-1 neighbours in one CSR, README "known limitations")
     uint32_t n_rows;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
         if (threadIdx.x < t.rows) {
             unsigned long long b, e;
             row_span(a, row, b, e);
-            if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);   // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
+            if (e < b || e > a.nnz || b < a.nn_lo || e - b > 0xffffffffull) atomicExch(a.err, 1);   // corrupt nn_ptr -> PGEOF_EINDEX, row left 0
             else if (e - b >= a.k_min && e > b) {                // pgeof.hpp:103
                 Moments m;
                 auto acc = [&](uint32_t, float dx, float dy, float dz) { m.add(dx, dy, dz); };
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kMsThreads, 3) multiscale_direct_kernel(const 
     unsigned long long b, e;
     row_span(a, row, b, e);
     uint32_t n_fit = 0, s = 0;                                  // scales of this pass the row is long enough for / written so far
-    if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);
+    if (e < b || e > a.nnz || b < a.nn_lo || e - b > 0xffffffffull) atomicExch(a.err, 1);
     else {
         const uint32_t len = (uint32_t)(e - b);
         while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kRows, 4) optimal_direct_kernel(const FeatArgs
     if (threadIdx.x < t.rows) {
         unsigned long long b, e;
         row_span(a, row, b, e);
-        if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);
+        if (e < b || e > a.nnz || b < a.nn_lo || e - b > 0xffffffffull) atomicExch(a.err, 1);
         else {
             const uint32_t len = (uint32_t)(e - b);
             if (len >= a.k_min && len >= a.k_min_search && len > 0) {                     // pgeof.hpp:272
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArg
     if (threadIdx.x < t.rows) {
         unsigned long long b, e;
         row_span(a, row, b, e);
-        if (e < b || e > a.nnz || e - b > 0xffffffffull) atomicExch(a.err, 1);
+        if (e < b || e > a.nnz || b < a.nn_lo || e - b > 0xffffffffull) atomicExch(a.err, 1);
         else {
             const uint32_t len = (uint32_t)(e - b);
             const uint32_t* __restrict__ p = a.nn + b;
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(256) row_count_kernel(const FeatArgs a, const 
     if (valid) {
         unsigned long long b, e;
         row_span(a, i, b, e);
-        if (e > b && b < a.nnz) {
+        if (e > b && b < a.nnz && b >= a.nn_lo) {
             const uint32_t first = __ldg(a.nn + b);
             if (first < a.n_xyz) {
                 const float4 p = __ldg(a.pts + first);
@@ -618,6 +619,11 @@ int env_int(const char* name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
+}  // namespace
+// set by the host pipeline (capi.cu) around a call that hands the kernels a slice nn[lo, nnz) of the caller's array
+thread_local unsigned long long g_nn_window_lo = 0;
+namespace {
+
 int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr nn_ptr, size_t n_rows,
               int eig_order, float* out, int* err)
 {
@@ -625,7 +631,7 @@ int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr 
     if (!nn_ptr.p64 && nnz > 0xffffffffull) { set_error("nn holds more than 2^32-1 entries: uint32 nn_ptr cannot address them (pass uint64 offsets or shard the rows)"); return PGEOF_EINVAL; }
     if (eig_order != PGEOF_EIG_LITERAL && eig_order != PGEOF_EIG_DOCUMENTED) { set_error("bad eig_order %d", eig_order); return PGEOF_EINVAL; }
     std::memset(a, 0, sizeof(*a));
-    a->n_xyz = (uint32_t)n_xyz; a->nn = nn; a->nnz = nnz; a->nn_ptr = nn_ptr.p32; a->nn_ptr64 = nn_ptr.p64; a->n_rows = (uint32_t)n_rows;
+    a->n_xyz = (uint32_t)n_xyz; a->nn = nn; a->nnz = nnz; a->nn_lo = g_nn_window_lo; a->nn_ptr = nn_ptr.p32; a->nn_ptr64 = nn_ptr.p64; a->n_rows = (uint32_t)n_rows;
     a->eig_order = eig_order; a->out = out; a->err = err; a->k_min = 1; a->k_step = 1; a->k_min_search = 1;
     a->tma_out = ((uintptr_t)out % 16 == 0);
     return PGEOF_OK;

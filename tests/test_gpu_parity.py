@@ -838,3 +838,28 @@ def test_torch_adaptor_frnn_and_spt_helpers_against_brute_force():
     assert torch.allclose(got[ok], ref[ok], atol=1e-6) and bool((ref[~ok] >= 0.2 - 1e-6).all())
     nb2, ds2 = ta.knn_2(xyz, xyz[:50], 5, r_max=10.0)
     assert bool((nb2[:, 0] == torch.arange(50, device="cuda")).all()) and bool((ds2[:, 0] == 0).all())
+
+
+def test_chunked_host_pipeline_matches_the_serial_flavour(monkeypatch):
+    """Host-buffer feature calls upload nn in chunks beside compute + download (capi.cu csr_pipeline): same bits as the serial
+    flavour, ragged rows and uint64 offsets included; a corrupt nn_ptr is refused either way."""
+    xyz = dense_lidar(150000, seed=31)
+    ridx, _ = pgeof.radius_search(xyz, xyz, 0.25, 48)
+    nn, nn_ptr = radius_csr(ridx)
+    kidx, _ = pgeof.knn_search(xyz, xyz, 40)
+    knn, kptr = knn_csr(kidx)
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PGEOF_HOST_CHUNK_MB", mode)            # 0: serial, 1: 1 MB slices -> 16 chunks
+        results[mode] = [pgeof.compute_features(xyz, nn, nn_ptr, 3),
+                         pgeof.compute_features(xyz, knn, kptr),
+                         pgeof.compute_features_multiscale(xyz, knn, kptr, [5, 20, 40]),
+                         pgeof.compute_features_optimal(xyz, knn, kptr, 1, 1, 10),
+                         pgeof.compute_features(xyz, nn, nn_ptr.astype(np.uint64), 3)]                 # 64-bit offsets (extension)
+        bad = nn_ptr.copy()
+        bad[len(bad) // 2] = bad[len(bad) // 2 - 1] - 1 if bad[len(bad) // 2 - 1] > 0 else bad[-1] + 5     # non-monotonic offsets
+        with pytest.raises((IndexError, ValueError)):
+            pgeof.compute_features(xyz, nn, bad)
+    for a, b in zip(results["0"], results["1"]):
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.abs(results["1"][0]).max() > 0
