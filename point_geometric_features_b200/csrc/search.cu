@@ -90,7 +90,13 @@ enum { ST_SHORT = 0, ST_OVER, ST_TIE, ST_REGION, ST_FIXED, ST_PASSES, ST_CANDS, 
 // ---------------------------------------------------------------------------------------
 // generic per-query kNN (one warp): collect the keys under an adaptive threshold
 // ---------------------------------------------------------------------------------------
-template <int CAP>
+// smallest geometric radius whose ball holds every point with key <= tau: tau_from_radius(radius_covering(tau)) >= tau
+__device__ __forceinline__ float radius_covering(u64 tau)
+{
+    return __fmul_ru(__fsqrt_ru(__fdiv_ru(key_d2(tau), 0.9999f)), 1.00001f);
+}
+
+template <int CAP, bool PREFETCH = false>
 __device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, float qy, float qz, uint32_t k, float target,
                                                 u64* keybuf, int lane, u64* tau_out, float r_hint = 0.f, bool* unsafe = nullptr)
 {
@@ -111,10 +117,10 @@ __device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, flo
         // a clipped grid (GridView::rmax_safe) only holds what balls up to that radius need: leave, the caller re-runs
         // the query on the full grid
         if (Rg > g.rmax_safe) { if (unsafe) *unsafe = true; *tau_out = 0; return 0; }
-        c = scan_ball<CAP, true>(g, qx, qy, qz, Rg, tau, keybuf, lane);
+        c = scan_ball<CAP, true, PREFETCH>(g, qx, qy, qz, Rg, tau, keybuf, lane);
         if (c < k) {
             tau_lo = tau; have_lo = true;
-            if (have_hi) { tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
+            if (have_hi) { tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = fminf(Rg_hi, radius_covering(tau)); }
             else {
                 const float f = fminf(fmaxf(cbrtf(1.2f * target / fmaxf((float)c, 0.5f)), 1.2f), 2.5f);
                 R *= f; Rg = R; tau = tau_from_radius(R);
@@ -130,7 +136,8 @@ __device__ __forceinline__ uint32_t knn_collect(const GridView& g, float qx, flo
             }
             // ... else bisect the key space between tau_lo (0: nothing is below it) and tau_hi:
             // always converges because keys are distinct (many duplicates / exact ties land here)
-            if (!shrunk) { have_lo = true; tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = Rg_hi; }
+            // (the rescan only has to cover the keys <= the new threshold: a smaller ball than the one that overflowed)
+            if (!shrunk) { have_lo = true; tau = tau_lo + (tau_hi - tau_lo) / 2; Rg = fminf(Rg_hi, radius_covering(tau)); }
         } else break;
     }
     *tau_out = tau;
@@ -834,7 +841,7 @@ __global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g,
         const float4 q4 = __ldg(a.queries + rec.x);
         u64 tau;
         bool unsafe = false;
-        const uint32_t c = knn_collect<CAP>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, __uint_as_float(rec.y), &unsafe);
+        const uint32_t c = knn_collect<CAP, true>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, __uint_as_float(rec.y), &unsafe);
         if (unsafe) {   // warp uniform
             if (lane == 0) a.unsafe_list[atomicAdd(a.unsafe_count, 1u)] = make_uint2(rec.x, 0u);
             continue;

@@ -58,7 +58,7 @@ __device__ __forceinline__ float axis_gap(float q, int c, int cq, float lo, floa
 // keybuf (first CAP only).  Returns how many keys were <= tau (may exceed CAP).
 // Rows of cells (fixed y, z) are contiguous spans of `pts`; 32 rows are resolved at a
 // time (one per lane) so the cell_start loads of a chunk are a single round trip.
-template <int CAP, bool STORE>
+template <int CAP, bool STORE, bool PREFETCH = false>
 __device__ __forceinline__ uint32_t scan_ball(const GridView& g, float qx, float qy, float qz, float R, u64 tau,
                                               u64* __restrict__ keybuf, int lane)
 {
@@ -94,25 +94,60 @@ __device__ __forceinline__ uint32_t scan_ball(const GridView& g, float qx, float
             }
         }
         unsigned nonempty = __ballot_sync(kFull, e > s);
-        while (nonempty) {
-            const int rr = __ffs(nonempty) - 1;
-            nonempty &= nonempty - 1;
-            const uint32_t s_r = __shfl_sync(kFull, s, rr), e_r = __shfl_sync(kFull, e, rr);
-            for (uint32_t base = s_r; base < e_r; base += 32) {
-                const uint32_t j = base + lane;
-                bool acc = false;
-                u64 key = 0;
-                if (j < e_r) {
-                    const float4 p = __ldg(g.pts + j);
-                    key = make_key(sqdist_f32(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
-                    acc = key <= tau;
+        // PREFETCH (the queued queries of a tile kernel: latency bound, 30 % of the stall samples wait for these loads on
+        // non-uniform clouds): the candidate loads are software pipelined -- the first 32 points of the NEXT row and the next
+        // 32 of the current one are requested before the current 32 are evaluated.  The all-queries kernels are issue bound
+        // (82 % issue-active at k = 100) and lose 10 % to the extra instructions, so they keep the plain loop.
+        auto visit = [&](uint32_t j, uint32_t e_r, const float4& p) {
+            bool acc = false;
+            u64 key = 0;
+            if (j < e_r) {
+                key = make_key(sqdist_f32(qx, qy, qz, p.x, p.y, p.z), __float_as_uint(p.w));
+                acc = key <= tau;
+            }
+            const unsigned m = __ballot_sync(kFull, acc);
+            if (STORE && acc) {
+                const uint32_t pos = count + __popc(m & lt);
+                if (pos < CAP) keybuf[pos] = key;
+            }
+            count += __popc(m);
+        };
+        if constexpr (!PREFETCH) {
+            while (nonempty) {
+                const int rr = __ffs(nonempty) - 1;
+                nonempty &= nonempty - 1;
+                const uint32_t s_r = __shfl_sync(kFull, s, rr), e_r = __shfl_sync(kFull, e, rr);
+                for (uint32_t base = s_r; base < e_r; base += 32) {
+                    const uint32_t j = base + lane;
+                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < e_r) p = __ldg(g.pts + j);
+                    visit(j, e_r, p);
                 }
-                const unsigned m = __ballot_sync(kFull, acc);
-                if (STORE && acc) {
-                    const uint32_t pos = count + __popc(m & lt);
-                    if (pos < CAP) keybuf[pos] = key;
+            }
+        } else {
+            float4 pf = make_float4(0.f, 0.f, 0.f, 0.f);      // prefetched head of the row about to be scanned
+            if (nonempty) {
+                const int r0 = __ffs(nonempty) - 1;
+                const uint32_t s0 = __shfl_sync(kFull, s, r0), e0 = __shfl_sync(kFull, e, r0);
+                if (s0 + lane < e0) pf = __ldg(g.pts + s0 + lane);
+            }
+            while (nonempty) {
+                const int rr = __ffs(nonempty) - 1;
+                nonempty &= nonempty - 1;
+                const uint32_t s_r = __shfl_sync(kFull, s, rr), e_r = __shfl_sync(kFull, e, rr);
+                float4 p = pf;
+                if (nonempty) {
+                    const int r2 = __ffs(nonempty) - 1;
+                    const uint32_t s2 = __shfl_sync(kFull, s, r2), e2 = __shfl_sync(kFull, e, r2);
+                    if (s2 + lane < e2) pf = __ldg(g.pts + s2 + lane);
                 }
-                count += __popc(m);
+                for (uint32_t base = s_r; base < e_r; base += 32) {
+                    const uint32_t j = base + lane;
+                    float4 pn = p;
+                    if (j + 32 < e_r) pn = __ldg(g.pts + j + 32);
+                    visit(j, e_r, p);
+                    p = pn;
+                }
             }
         }
     }
