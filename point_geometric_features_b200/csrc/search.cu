@@ -411,8 +411,12 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
     float* const s_rmul = s_hint + 32;       // this lane's factor on the density-seeded radius
     uint32_t* const s_retry = reinterpret_cast<uint32_t*>(s_hint + 64);   // bits 0-1: re-queues so far, bits 2-3: class (0 first try, 1 grow, 2 shrink)
     *s_hint = 0.f; *s_rmul = 1.f; *s_retry = 0u;
-    for (int pass = 0; LOCK ? __syncthreads_or(remaining != 0) != 0 : remaining != 0; ++pass) {
-        if (LOCK && !remaining) { PGEOF_LOCK_BARRIER(); PGEOF_LOCK_BARRIER(); continue; }
+    // LOCK: one round of the CTA = every warp's pass.  The barrier in front of the key load doubles as the vote on another
+    // round (does any warp still hold queries for a later pass?), so a round costs two barriers, not three.
+    bool more = true;
+#define PGEOF_LOCK_VOTE() do { if (LOCK) more = __syncthreads_or(remaining != 0) != 0; } while (0)
+    for (int pass = 0; LOCK ? more : remaining != 0; ++pass) {
+        if (LOCK && !remaining) { PGEOF_LOCK_VOTE(); PGEOF_LOCK_BARRIER(); continue; }
         // ---- the lanes of this pass: queries in the (y, z) cell row of the first remaining lane ----
         const int leader = __ffs(remaining) - 1;
         const uint32_t lrow = __shfl_sync(kFull, rowid, leader);
@@ -423,7 +427,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         if (pass >= Cfg::MAX_PASSES) {
             slow |= active;
             if (a.stats && lane == 0) atomicAdd(a.stats + ST_REGION, (unsigned long long)__popc(active));
-            PGEOF_LOCK_BARRIER(); PGEOF_LOCK_BARRIER();
+            PGEOF_LOCK_VOTE(); PGEOF_LOCK_BARRIER();
             continue;
         }
 
@@ -527,7 +531,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             remaining |= active & ~keep;
             active = keep;
         }
-        if (!active) { PGEOF_LOCK_BARRIER(); PGEOF_LOCK_BARRIER(); continue; }
+        if (!active) { PGEOF_LOCK_VOTE(); PGEOF_LOCK_BARRIER(); continue; }
 
         // ---- stage the region: one 1-D TMA bulk copy per row, all rows in flight at once ---------
         __syncwarp();
@@ -613,7 +617,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
         uint32_t nvalid = 0;                   // radius mode: kept entries whose defined distance is < r^2
         {
             uint32_t v[NLOAD];
-            PGEOF_LOCK_BARRIER();
+            PGEOF_LOCK_VOTE();
 #pragma unroll
             for (int i = 0; i < NLOAD; ++i) {
                 const uint32_t w = wbase[i * S];
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
                     uint32_t b = 0;
-#pragma unroll 4
+#pragma unroll 16
                     for (int j = 0; j < 32; ++j) {
                         const int i = r * 32 + j;
                         const uint32_t slot = plane_d[i * S] & Cfg::SLOT_MASK;
