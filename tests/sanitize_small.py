@@ -42,3 +42,25 @@ b200.knn_features(t, 50)
 b200.knn_features(t, 9, 1, True)
 torch.cuda.synchronize()
 print("sanitize_small ok")
+# paths added in round 2: any k (global-scratch kernel), CSR-native kNN, 64-bit offsets, the chunked host pipeline, the optimal-k
+# scan at k = 100, and -- SAN_VARIANTS=1 -- the kernels kept behind switches (pair, rolled rebuild, 160-key tile, no lock step)
+pgeof.knn_search(xyz, xyz[:200], 700)
+pgeof.radius_search(xyz, xyz[:200], 5.0, 600)
+b200.knn_search_csr(xyz, xyz, 12)
+i100, _ = pgeof.knn_search(big, big, 100)
+n100, p100 = synth.knn_csr(i100)
+pgeof.compute_features_optimal(big, n100, p100, 1, 1, 10)
+pgeof.compute_features(big, n100, p100.astype(np.uint64))
+os.environ["PGEOF_HOST_CHUNK_MB"] = "1"
+pgeof.compute_features(big, n100, p100)
+pgeof.compute_features_multiscale(big, n100, p100, [10, 50, 100])
+del os.environ["PGEOF_HOST_CHUNK_MB"]
+if os.environ.get("SAN_VARIANTS"):
+    for name in ("PGEOF_KNN_PAIR", "PGEOF_KNN_ROLLED", "PGEOF_KNN_TILE128", "PGEOF_KNN_LOCK", "PGEOF_OPTIMAL_SCAN"):
+        os.environ[name] = "0" if name in ("PGEOF_KNN_LOCK", "PGEOF_OPTIMAL_SCAN") else "1"
+        pgeof.knn_search(big, big, 50)
+        pgeof.knn_search(big, big[:20000], 100)
+        pgeof.compute_features_optimal(big, n100, p100, 1, 1, 10)
+        del os.environ[name]
+torch.cuda.synchronize()
+print("sanitize_small round-2 paths ok")
