@@ -267,6 +267,84 @@ __device__ __forceinline__ void warp_bitonic_sort(u64 (&v)[M], int lane)
     }
 }
 
+// The same network on 32-bit keys (one SHFL + one min/max per element and stage instead of two SHFLs and a 64-bit compare).
+template <int M>
+__device__ __forceinline__ void warp_bitonic_sort32(uint32_t (&v)[M], int lane)
+{
+#pragma unroll
+    for (int size = 2; size <= 32 * M; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int ms = stride >> 5;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    if ((m & ms) == 0) {
+                        const bool asc = (((m << 5) & size) == 0);
+                        const uint32_t a = v[m], b = v[m | ms];
+                        v[m] = asc ? min(a, b) : max(a, b);
+                        v[m | ms] = asc ? max(a, b) : min(a, b);
+                    }
+                }
+            } else {
+                const bool lower = (lane & stride) == 0;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const uint32_t o = __shfl_xor_sync(kFull, v[m], stride);
+                    const bool asc = ((((m << 5) | lane) & size) == 0);
+                    v[m] = (lower == asc) ? min(v[m], o) : max(v[m], o);
+                }
+            }
+        }
+    }
+}
+
+// v holds 32 * M keys at element index m * 32 + lane: true iff they ascend
+template <int M>
+__device__ __forceinline__ bool warp_is_sorted(const u64 (&v)[M], int lane)
+{
+    bool inv = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        u64 nxt = __shfl_down_sync(kFull, v[m], 1);
+        if (m + 1 < M) { const u64 head = __shfl_sync(kFull, v[m + 1], 0); if (lane == 31) nxt = head; }
+        else if (lane == 31) nxt = kKeyMax;
+        inv = inv || nxt < v[m];
+    }
+    return __ballot_sync(kFull, inv) == 0u;
+}
+
+// one odd-even transposition round (both parities) on the same layout: fixes isolated adjacent swaps
+template <int M>
+__device__ __forceinline__ void warp_transpose_round(u64 (&v)[M], int lane)
+{
+    // pairs (e, e + 1), e even: lanes (2i, 2i + 1) of the same register
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const u64 o = __shfl_xor_sync(kFull, v[m], 1);
+        const bool low = (lane & 1) == 0;
+        v[m] = (low == (o < v[m])) ? o : v[m];
+    }
+    // pairs (e, e + 1), e odd: lanes (2i + 1, 2i + 2); lane 31 pairs with lane 0 of the next register
+    u64 w[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        u64 o = __shfl_sync(kFull, v[m], (lane & 1) ? lane + 1 : lane - 1);      // (lanes 0 and 31 are overridden below)
+        bool have = true;
+        if (lane == 31) { have = m + 1 < M; if (m + 1 < M) o = 0; }
+        if (lane == 0) { have = m > 0; }
+        u64 head = 0, tail = 0;
+        if (m + 1 < M) head = __shfl_sync(kFull, v[m + 1], 0);
+        if (m > 0) tail = __shfl_sync(kFull, v[m - 1], 31);
+        if (lane == 31 && m + 1 < M) o = head;
+        if (lane == 0 && m > 0) o = tail;
+        const bool low = (lane & 1) == 1;                                         // the odd lane holds the lower element of the pair
+        w[m] = (have && (low == (o < v[m]))) ? o : v[m];
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) v[m] = w[m];
+}
+
 // Thread-local sorting networks on N 32-bit keys held in registers.  Every index is a compile-time
 // constant after unrolling, so v[] never leaves the register file; a compare-exchange is one
 // unsigned min / max pair (no predicates, no shuffles) and the 32 lanes of a warp sort 32
