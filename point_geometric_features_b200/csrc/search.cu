@@ -82,6 +82,11 @@ struct SearchArgs {
     uint32_t* tmp_idx;       // [tmp_cap][k] neighbour rows of the queries the tile kernel queued
     uint32_t* tmp_rows;      // [tmp_cap] their row ids
     uint32_t tmp_cap;
+    // queued queries whose ball spans many cells of this grid (sparse parts of a cloud whose cell edge was sized for its dense
+    // surfaces) are deferred to a second run on a coarser grid: (query position, bits(start radius)) + counter, or null
+    uint2* defer_list;
+    uint32_t* defer_count;
+    float r_split;           // start radius above which a queued query is deferred
 };
 
 // tile-kernel counters: why queries left the fast path, and how much work the fast path did
@@ -856,9 +861,22 @@ __global__ void __launch_bounds__(kWarps * 32) knn_slow_kernel(const GridView g,
     for (uint32_t w = blockIdx.x * kWarps + warp; w < n; w += gridDim.x * kWarps) {
         const uint2 rec = a.slow_list[w];
         const float4 q4 = __ldg(a.queries + rec.x);
+        float r_start = __uint_as_float(rec.y);
+        if (a.defer_list) {
+            if (!(r_start > 0.f)) {   // no hint (the region did not fit the tile kernel at all): the density seed of knn_collect
+                uint32_t n27, cells27;
+                block27_count(g, q4.x, q4.y, q4.z, lane, &n27, &cells27);
+                const float rho = fmaxf((float)n27, 1.f) / ((float)max(cells27, 1u) * g.hx * g.h * g.h);
+                r_start = cbrtf(a.target / (4.18879f * rho)) + bbox_distance(g, q4.x, q4.y, q4.z);
+            }
+            if (r_start > a.r_split) {   // warp uniform: every row of cells this ball crosses holds a handful of points here
+                if (lane == 0) a.defer_list[atomicAdd(a.defer_count, 1u)] = make_uint2(rec.x, __float_as_uint(r_start));
+                continue;
+            }
+        }
         u64 tau;
         bool unsafe = false;
-        const uint32_t c = knn_collect<CAP, true>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, __uint_as_float(rec.y), &unsafe);
+        const uint32_t c = knn_collect<CAP, true>(g, q4.x, q4.y, q4.z, k, a.target, keybuf, lane, &tau, r_start, &unsafe);
         if (unsafe) {   // warp uniform
             if (lane == 0) a.unsafe_list[atomicAdd(a.unsafe_count, 1u)] = make_uint2(rec.x, 0u);
             continue;
@@ -1501,7 +1519,7 @@ int launch_search(const GridView& g, const SearchArgs& a, cudaStream_t stream)
 }
 
 template <int NOUT, int NEXTRA, int NWARPS = 2, int MODE = SEARCH_KNN, bool FUSED = false, bool LOCK = true, bool ROLLED = false>
-int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
+int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream, bool run_slow = true)
 {
     using Cfg = TileCfg<NOUT, NEXTRA, NWARPS>;
     const size_t smem = (size_t)Cfg::WARPS * Cfg::SMEM_WARP_BYTES;
@@ -1511,7 +1529,7 @@ int launch_tile(const GridView& g, const SearchArgs& a, cudaStream_t stream)
     {
         KernelTimer timer(MODE == SEARCH_KNN ? "knn_search" : "radius_search", stream);
         kern<<<blocks, Cfg::WARPS * 32, smem, stream>>>(g, a);
-        if (MODE == SEARCH_KNN) knn_slow_kernel<NOUT><<<sm_count() * 4, kWarps * 32, 0, stream>>>(g, a);
+        if (MODE == SEARCH_KNN) { if (run_slow) knn_slow_kernel<NOUT><<<sm_count() * 4, kWarps * 32, 0, stream>>>(g, a); }
         else search_list_kernel<NOUT, SEARCH_RADIUS><<<sm_count() * 4, kWarps * 32, (size_t)kWarps * SearchCfg<NOUT, SEARCH_RADIUS>::CAP * sizeof(u64), stream>>>(g, a);
     }
     PGEOF_LAUNCH_CHECK();
@@ -1656,9 +1674,13 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
             PGEOF_CUDA(cudaMemsetAsync(stats.ptr, 0, ST_N * sizeof(unsigned long long), stream));
             a.stats = stats.as<unsigned long long>();
         }
+        // kNN on the full grid through the default tile kernels: the queued queries run from here (two levels), not from launch_tile
+        const bool two_level = mode == SEARCH_KNN && !clipped && k <= 64 && !pair && env_float("PGEOF_KNN_TWO_LEVEL", 1.f) != 0.f &&
+                               env_float("PGEOF_KNN_ROLLED", 0.f) == 0.f && env_float("PGEOF_KNN_LOCK", 1.f) != 0.f && env_float("PGEOF_KNN_WARPS", 4.f) == 4.f;
+        const bool two_level_now = two_level;
         int st;
         if (mode == SEARCH_RADIUS) st = k <= 32 ? launch_tile<32, 32, 2, SEARCH_RADIUS>(grid.view, a, stream) : launch_tile<64, 32, 4, SEARCH_RADIUS>(grid.view, a, stream);
-        else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream);
+        else if (k <= 32) st = launch_tile<32, 32>(grid.view, a, stream, !two_level);
         else if (pair && k <= 64) {
             const int variant = (int)env_float("PGEOF_PAIR_VARIANT", 0.f);
             st = variant == 1 ? launch_pair<48, 32, 3, 640, 3>(grid.view, a, stream)
@@ -1668,7 +1690,44 @@ int search_run(SearchMode mode, const float* data, size_t n_data, const float* q
         else if (k > 64) st = launch_tile<128, 32, 5, SEARCH_KNN, false, true, true>(grid.view, a, stream);
         else if (env_float("PGEOF_KNN_ROLLED", 0.f) != 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, true, true>(grid.view, a, stream);   // A/B switches
         else if (env_float("PGEOF_KNN_LOCK", 1.f) == 0.f) st = launch_tile<64, 32, 4, SEARCH_KNN, false, false>(grid.view, a, stream);
-        else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream) : launch_tile<64, 32>(grid.view, a, stream);
+        else st = env_float("PGEOF_KNN_WARPS", 4.f) == 4.f ? launch_tile<64, 32, 4>(grid.view, a, stream, !two_level) : launch_tile<64, 32>(grid.view, a, stream);
+        // Two-level handling of the queued queries (non-uniform clouds): the cell edge is sized for where most points live, so in
+        // the sparse parts a ball crosses hundreds of cell rows that hold a handful of points each and the warp-per-query routine
+        // spends its time walking rows.  Those queries (start radius > 1.5 cell edges) are deferred by the first run and, if there
+        // are enough of them to pay for a second index, answered on a grid with 3x the cell edge (sweep: profiles/r2_summary.md).  Exact either way (the routine
+        // is exact on any grid); uniform clouds defer nothing and pay one 4-byte read-back.
+        if (st == PGEOF_OK && two_level_now) {
+            DeviceBuffer defer;
+            PGEOF_TRY(defer.alloc(16 + n_query * sizeof(uint2), stream));
+            a.defer_count = defer.as<uint32_t>();
+            a.defer_list = reinterpret_cast<uint2*>(defer.as<unsigned char>() + 16);
+            a.r_split = env_float("PGEOF_KNN_SPLIT", 1.5f) * grid.view.h;
+            PGEOF_CUDA(cudaMemsetAsync(a.defer_count, 0, 16, stream));
+            auto run_list = [&](const GridView& gv, const SearchArgs& args) -> int {
+                KernelTimer timer("knn_search", stream);
+                if (k <= 32) knn_slow_kernel<32><<<sm_count() * 4, kWarps * 32, 0, stream>>>(gv, args);
+                else knn_slow_kernel<64><<<sm_count() * 4, kWarps * 32, 0, stream>>>(gv, args);
+                PGEOF_LAUNCH_CHECK();
+                return PGEOF_OK;
+            };
+            PGEOF_TRY(run_list(grid.view, a));
+            uint32_t n_defer = 0;
+            PGEOF_CUDA(cudaMemcpyAsync(&n_defer, a.defer_count, sizeof(n_defer), cudaMemcpyDeviceToHost, stream));
+            PGEOF_CUDA(cudaStreamSynchronize(stream));
+            if (n_defer) {
+                SearchArgs b = a;
+                b.slow_list = a.defer_list;
+                b.slow_count = a.defer_count;
+                b.defer_list = nullptr;
+                b.defer_count = nullptr;
+                Grid coarse;
+                const bool build = n_defer >= (uint32_t)env_float("PGEOF_KNN_COARSE_MIN", 50000.f);
+                if (build) PGEOF_TRY(grid_build(data, n_data, env_float("PGEOF_KNN_COARSE", 3.f) * grid.view.h, 0.f, xf, stream, &coarse));
+                PGEOF_TRY(run_list(build ? coarse.view : grid.view, b));
+                if (env_float("PGEOF_KNN_STATS", 0.f) != 0.f)
+                    std::fprintf(stderr, "[pgeof knn tile] deferred %u queued queries to a %s grid (cell edge %.3f)\n", n_defer, build ? "coarser" : "the same", build ? coarse.view.h : grid.view.h);
+            }
+        }
         uint32_t n_unsafe = 0;
         if (st == PGEOF_OK && clipped && mode == SEARCH_KNN) {
             PGEOF_CUDA(cudaMemcpyAsync(&n_unsafe, a.unsafe_count, sizeof(n_unsafe), cudaMemcpyDeviceToHost, stream));

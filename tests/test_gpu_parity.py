@@ -701,7 +701,7 @@ def test_optimal_k_against_the_float32_arithmetic_of_the_reference():
         assert (margin32[differ] < 1e-5).all()
 
 
-SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"), ("PGEOF_KNN_TILE128", "1"),
+SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"), ("PGEOF_KNN_TILE128", "1"), ("PGEOF_KNN_TWO_LEVEL", "0"),
             ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0")]
 
 
@@ -863,3 +863,19 @@ def test_chunked_host_pipeline_matches_the_serial_flavour(monkeypatch):
     for a, b in zip(results["0"], results["1"]):
         np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
     assert np.abs(results["1"][0]).max() > 0
+
+
+def test_knn_sparse_queued_queries_on_the_coarser_grid(monkeypatch):
+    """Non-uniform cloud: the queued queries of the sparse parts (scatter blobs, poles) are deferred to a grid with 4x the cell
+    edge (search.cu: two-level handling).  Bit-exact with and without the second level, for both tile kernels."""
+    monkeypatch.setenv("PGEOF_KNN_COARSE_MIN", "1")              # build the second grid however few queries were deferred
+    xyz = dense_lidar(300000, seed=41)
+    rows = np.random.default_rng(42).choice(len(xyz), 4000, replace=False)
+    for k in (20, 50):
+        idx, d2 = pgeof.knn_search(xyz, xyz, k)
+        _assert_search_equal((idx[rows], d2[rows]), cpu.knn_search(xyz, xyz[rows], k))
+        monkeypatch.setenv("PGEOF_KNN_TWO_LEVEL", "0")
+        idx0, d20 = pgeof.knn_search(xyz, xyz, k)
+        monkeypatch.delenv("PGEOF_KNN_TWO_LEVEL")
+        np.testing.assert_array_equal(idx, idx0)
+        np.testing.assert_array_equal(d2.view(np.uint32), d20.view(np.uint32))
