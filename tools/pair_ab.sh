@@ -1,4 +1,5 @@
 #!/bin/bash
-for sp in 1.2 1.7 2.5; do for co in 2 3 4 6; do
-  PGEOF_KNN_SPLIT=$sp PGEOF_KNN_COARSE=$co PGEOF_KNN_STATS=1 python tools/lidar_probe.py 2>&1 | grep -E "deferred|lidar kNN" | tail -2 | tr '\n' ' '; echo " split=$sp coarse=$co"
-done; done
+for v in "PGEOF_KNN_TWO_LEVEL=0 PGEOF_KNN_LOCK=1" "PGEOF_KNN_TWO_LEVEL=0 PGEOF_KNN_LOCK=0" "PGEOF_KNN_TWO_LEVEL=0 PGEOF_KNN_FLAGS=2" "PGEOF_KNN_TWO_LEVEL=1"; do
+  env $v python tools/lidar_probe.py 2>&1 | grep -E "lidar kNN" | tail -1 | tr '\n' ' '; echo " $v"
+done
+PGEOF_KNN_TWO_LEVEL=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv -k regex:"knn_tile|knn_slow|cell_count|scatter_kernel" python tools/lidar_probe.py 2>/dev/null | grep -E "knn_tile|knn_slow|cell_count|scatter" | tail -8 | awk -F"\",\"" '{print $5, $NF}' | cut -c1-120
