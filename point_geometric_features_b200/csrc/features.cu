@@ -379,7 +379,38 @@ __device__ __forceinline__ float eigentropy_fast(float l0, float l1, float l2)
     return -0.69314718056f * (e0 * __log2f(e0 + eps) + e1 * __log2f(e1 + eps) + e2 * __log2f(e2 + eps));
 }
 
-template <int MINB>
+// Filter eigenvalues in closed form (trigonometric solution of the characteristic cubic, float, MUFU cosine): ~90 instructions
+// against ~250 for three Jacobi sweeps.  The form loses digits where two eigenvalues coincide (phi = acos(r) / 3 is ill
+// conditioned at |r| -> 1), so it returns a bound on the entropy error it may have caused and the caller widens its
+// too-close-to-call window by it (the double evaluation then decides, as for any near tie): k_opt stays exact.
+// Input scaled to max |a_ij| = 1, so the trace is >= 1; w is unsorted and clamped at 0.
+__device__ __forceinline__ float eigvals3_closed_f32(float a00, float a01, float a02, float a11, float a12, float a22, float (&w)[3])
+{
+    const float q = (a00 + a11 + a22) * (1.f / 3.f);
+    const float b00 = a00 - q, b11 = a11 - q, b22 = a22 - q;
+    const float off2 = fmaf(a01, a01, fmaf(a02, a02, a12 * a12));
+    const float p2 = fmaf(b00, b00, fmaf(b11, b11, fmaf(b22, b22, 2.f * off2)));
+    if (!(p2 > 1e-30f)) { w[0] = w[1] = w[2] = fmaxf(q, 0.f); return 1e-6f; }
+    const float ip = rsqrtf(p2 * (1.f / 6.f));
+    const float p = p2 * (1.f / 6.f) * ip;
+    const float c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = a01 * ip, c02 = a02 * ip, c12 = a12 * ip;
+    float r = 0.5f * (c00 * fmaf(c11, c22, -c12 * c12) - c01 * fmaf(c01, c22, -c12 * c02) + c02 * fmaf(c01, c12, -c11 * c02));
+    r = fminf(1.f, fmaxf(-1.f, r));
+    const float phi = acosf(r) * (1.f / 3.f);
+    const float hi = fmaf(2.f * p, __cosf(phi), q);
+    const float lo = fmaf(2.f * p, __cosf(phi + 2.0943951f), q);
+    const float mid = 3.f * q - hi - lo;
+    w[0] = fmaxf(lo, 0.f); w[1] = fmaxf(mid, 0.f); w[2] = fmaxf(hi, 0.f);
+    // |dr| <= 4e-6 (the determinant of entries <= sqrt(6) in float, rsqrt and cancellation included, four times over);
+    // dphi = dr / (3 sqrt(1 - r^2)), never more than sqrt(2 dr) / 3; an eigenvalue moves by <= 2 p (dphi + cosine error 5e-7)
+    // plus the rounding of the inputs (1e-6 of the unit norm); the entropy by <= 3 (|ln 1e-3| + 1) = 24 times that over the
+    // trace (>= 1).
+    const float dr = 4e-6f;
+    const float dphi = fminf(dr * rsqrtf(fmaxf(fmaf(-r, r, 1.f), 1e-12f)), 2.9e-3f) * (1.f / 3.f);
+    return 24.f * (2.f * p * (dphi + 5e-7f) + 1e-6f);
+}
+
+template <int MINB, bool CLOSED>
 __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArgs a)
 {
     __shared__ uint32_t s_rowid[kRows];
@@ -409,7 +440,7 @@ __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArg
                 const float4 o = __ldg(a.pts + i0);
                 MomentsD m;
                 double best_c[6] = {0, 0, 0, 0, 0, 0}, best_h64 = 0.0;
-                float best_h32 = 0.f;
+                float best_h32 = 0.f, best_err = 0.f;
                 uint32_t best_k = len;
                 bool have64 = false;
                 uint32_t rem = 0;                                                        // k % k_step, kept incrementally
@@ -453,8 +484,14 @@ __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArg
                         float a00 = (float)c[0], a01 = (float)c[1], a02 = (float)c[2], a11 = (float)c[3], a12 = (float)c[4], a22 = (float)c[5];
                         float scale = fmaxf(fmaxf(fabsf(a00), fabsf(a11)), fabsf(a22));
                         scale = fmaxf(scale, fmaxf(fmaxf(fabsf(a01), fabsf(a02)), fabsf(a12)));
-                        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-                        if (scale > 0.f) {
+                        float w0 = 0.f, w1 = 0.f, w2 = 0.f, err = 0.f;
+                        if (CLOSED && scale > 0.f) {
+                            const float inv = __frcp_rn(scale);
+                            float w[3];
+                            err = eigvals3_closed_f32(a00 * inv, a01 * inv, a02 * inv, a11 * inv, a12 * inv, a22 * inv, w);
+                            w0 = w[0] * scale; w1 = w[1] * scale; w2 = w[2] * scale;
+                        }
+                        if (!CLOSED && scale > 0.f) {
                             const float inv = __frcp_rn(scale);
                             a00 *= inv; a01 *= inv; a02 *= inv; a11 *= inv; a12 *= inv; a22 *= inv;
 #define PGEOF_ROTF(app, aqq, apq, arp, arq)                                                   \
@@ -481,17 +518,19 @@ __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArg
                             w0 = fmaxf(a00 * scale, 0.f); w1 = fmaxf(a11 * scale, 0.f); w2 = fmaxf(a22 * scale, 0.f);
                         }
                         const float h32 = eigentropy_fast(w0, w1, w2);
-                        bool take = k == k0 || h32 < best_h32 - kOptMargin;
+                        // window inside which float cannot call it: Jacobi values are good to ~5e-5, the closed form to its own bound
+                        const float margin = CLOSED ? 1e-4f + err + best_err : kOptMargin;
+                        bool take = k == k0 || h32 < best_h32 - margin;
                         bool exact = false;
                         double h64 = 0.0;
-                        if (!take && !(h32 > best_h32 + kOptMargin)) {                   // too close to call in float
+                        if (!take && !(h32 > best_h32 + margin)) {                       // too close to call in float
                             if (!have64) { best_h64 = entropy_f64_nv(best_c[0], best_c[1], best_c[2], best_c[3], best_c[4], best_c[5]); have64 = true; }
                             h64 = entropy_f64_nv(c[0], c[1], c[2], c[3], c[4], c[5]);
                             take = h64 < best_h64;                                       // pgeof.hpp:289
                             exact = true;
                         }
                         if (take) {
-                            best_k = k; best_h32 = h32; best_h64 = h64; have64 = exact;
+                            best_k = k; best_h32 = h32; best_h64 = h64; have64 = exact; best_err = err;
 #pragma unroll
                             for (int z = 0; z < 6; ++z) best_c[z] = c[z];
                         }
@@ -767,9 +806,19 @@ int features_optimal_run(const float* xyz, size_t n_xyz, const uint32_t* nn, siz
     {
         KernelTimer timer("optimal", stream);
         // PGEOF_OPTIMAL_SCAN = 0: the first version (walker with the evaluation out of line), kept as an A/B switch
-        const int scan = env_int("PGEOF_OPTIMAL_SCAN", 1);
-        // 6 CTAs of 128 rows per SM (80 registers): measured 26.8 / 23.4 / 22.5 / 23.0 ms per 10 M rows at 4 / 5 / 6 / 8
-        if (scan != 0) optimal_scan_kernel<6><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        const int scan = env_int("PGEOF_OPTIMAL_SCAN", 2);   // 2: closed-form float filter, 1: Jacobi float filter
+        // CTAs of 128 rows per SM.  Jacobi filter: 26.8 / 23.4 / 22.5 / 23.0 ms per 10 M rows at 4 / 5 / 6 / 8 -> 6 (80 registers);
+        // closed-form filter: 11.9 / 11.2 / 13.2 / 17.4 ms -> 5 (96 registers)
+        if (scan == 1) optimal_scan_kernel<6, false><<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
+        else if (scan != 0) {
+            const unsigned blocks = (unsigned)((n_rows + kRows - 1) / kRows);
+            switch (env_int("PGEOF_OPTIMAL_CTAS", 5)) {
+                case 4: optimal_scan_kernel<4, true><<<blocks, kRows, 0, stream>>>(a); break;
+                case 6: optimal_scan_kernel<6, true><<<blocks, kRows, 0, stream>>>(a); break;
+                case 8: optimal_scan_kernel<8, true><<<blocks, kRows, 0, stream>>>(a); break;
+                default: optimal_scan_kernel<5, true><<<blocks, kRows, 0, stream>>>(a); break;
+            }
+        }
         else optimal_direct_kernel<<<(unsigned)((n_rows + kRows - 1) / kRows), kRows, 0, stream>>>(a);
     }
     PGEOF_LAUNCH_CHECK();
