@@ -702,7 +702,8 @@ def test_optimal_k_against_the_float32_arithmetic_of_the_reference():
 
 
 SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"), ("PGEOF_KNN_TILE128", "1"), ("PGEOF_KNN_TWO_LEVEL", "0"),
-            ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0")]
+            ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0"),
+            ("PGEOF_OPTIMAL_SCAN", "0"), ("PGEOF_OPTIMAL_SCAN", "1"), ("PGEOF_OPTIMAL_CTAS", "6")]
 
 
 @pytest.mark.parametrize("name,value", SWITCHES)
@@ -722,7 +723,7 @@ def test_every_switch_leaves_the_results_unchanged(name, value, monkeypatch):
         ri, rd = pgeof.radius_search(t, t, 6.0, 40)
         ptr = (torch.arange(len(xyz) + 1, device="cuda") * 50).to(torch.uint32)
         f = pgeof.compute_features(t, idx.view(-1), ptr)
-        ms = pgeof.compute_features_multiscale(t, idx.view(-1), ptr, [10, 50])
+        ms = pgeof.compute_features_multiscale(t, idx.view(-1), ptr, [10, 13, 20, 50])
         op = pgeof.compute_features_optimal(t, idx.view(-1), ptr, 1, 1, 10)
         fu = b200.knn_features(t, 50)
         got = [x.cpu().numpy().view(np.uint32) for x in (idx, d2, qi, qd, wi, wd, ri, rd, f, ms, op, fu)]
