@@ -324,6 +324,40 @@ def test_optimal_ragged_rows_and_gates():
     np.testing.assert_array_equal(opt[sure, 11], ref[sure, 11])
 
 
+@pytest.mark.parametrize("shape", ["plane", "line", "blobs", "lattice", "tiny", "far", "needle"])
+def test_optimal_k_exact_on_degenerate_and_scaled_neighbourhoods(shape):
+    """The optimal-k scan filters with closed-form float eigenvalues, which lose digits exactly where eigenvalues coincide or
+    vanish; its a-posteriori bound must hand every such case to the double evaluation: k_opt exact (pgeof.hpp:286-289) on
+    planes / lines (zero eigenvalues), isotropic blobs and a lattice (coincident eigenvalues), and on clouds scaled or
+    shifted by orders of magnitude."""
+    rng = np.random.default_rng(33)
+    n = 20000
+    if shape == "plane":
+        xyz = np.c_[rng.uniform(0, 30, (n, 2)), np.zeros(n)]
+    elif shape == "line":
+        xyz = np.c_[rng.uniform(0, 3000, n), np.full(n, 2.0), np.full(n, -1.0)]
+    elif shape == "blobs":
+        xyz = rng.normal(0, 1, (n, 3)) + rng.integers(0, 8, (n, 1)) * 10.0
+    elif shape == "lattice":
+        g = np.arange(28, dtype=np.float64)
+        xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)[:n]
+    elif shape == "tiny":
+        xyz = rng.uniform(0, 1, (n, 3)) * 1e-4
+    elif shape == "far":
+        xyz = rng.uniform(0, 40, (n, 3)) + 3000.0
+    else:                                                                            # thin needles: one large, two small close eigenvalues
+        xyz = np.c_[rng.uniform(0, 2000, n), rng.normal(0, 1e-2, n), rng.normal(0, 1e-2, n)]
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    idx, _ = pgeof.knn_search(xyz, xyz, 60)
+    nn, nn_ptr = knn_csr(idx)
+    for k_min_search in (3, 10):
+        opt = pgeof.compute_features_optimal(xyz, nn, nn_ptr, 1, 1, k_min_search)
+        ref, margin = cpu.compute_features_optimal(xyz, nn, nn_ptr, 1, 1, k_min_search, return_margin=True)
+        sure = margin > 1e-9
+        print("optimal-k %s (k_min_search %d): %.4f of the rows decided in float64 by more than 1e-9" % (shape, k_min_search, sure.mean()))
+        np.testing.assert_array_equal(opt[sure, 11], ref[sure, 11])
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("order", ORDERS)
 def test_selected_fused_radius_features(dtype, order):
