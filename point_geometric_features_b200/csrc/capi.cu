@@ -585,17 +585,6 @@ int pgeof_radius_search(const float* data, size_t n_data, const float* query, si
 // call only compacts it.  If the second call does not match the parked search (other arguments, other thread) it searches
 // again -- same result, one search slower.
 
-__global__ void padded_row_count_kernel(const int32_t* __restrict__ idx, size_t n_rows, uint32_t max_knn, uint32_t* __restrict__ counts)
-{
-    const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n_rows) return;
-    const int lane = threadIdx.x & 31;
-    uint32_t c = 0;
-    for (uint32_t j = lane; j < max_knn; j += 32) c += __ldg(idx + row * max_knn + j) >= 0 ? 1u : 0u;   // hits are a prefix of the row
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) counts[row] = c;
-}
-
 __global__ void padded_compact_kernel(const int32_t* __restrict__ idx, size_t n_rows, uint32_t max_knn, const uint32_t* __restrict__ nn_ptr,
                                       uint32_t* __restrict__ nn)
 {
@@ -604,6 +593,34 @@ __global__ void padded_compact_kernel(const int32_t* __restrict__ idx, size_t n_
     const int lane = threadIdx.x & 31;
     const uint32_t b = __ldg(nn_ptr + row), len = __ldg(nn_ptr + row + 1) - b;
     for (uint32_t j = lane; j < len; j += 32) nn[(size_t)b + j] = (uint32_t)__ldg(idx + row * max_knn + j);
+}
+
+// max_knn <= 64: a warp moves 8 rows, their (up to) 16 loads in flight together (one row per warp ran at a quarter of the
+// memory rate: one load, one store, exit)
+__global__ void __launch_bounds__(256) padded_compact8_kernel(const int32_t* __restrict__ idx, size_t n_rows, uint32_t max_knn,
+                                                              const uint32_t* __restrict__ nn_ptr, uint32_t* __restrict__ nn)
+{
+    const size_t r0 = ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8;
+    if (r0 >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = (lane < 9 && r0 + lane <= n_rows) ? __ldg(nn_ptr + r0 + lane) : 0u;
+    uint32_t b[8], len[8], lo[8], hi[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        b[u] = __shfl_sync(0xffffffffu, p, u);
+        len[u] = r0 + u < n_rows ? __shfl_sync(0xffffffffu, p, u + 1) - b[u] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int32_t* src = idx + (r0 + u) * max_knn;
+        lo[u] = (uint32_t)lane < len[u] ? (uint32_t)__ldg(src + lane) : 0u;
+        hi[u] = (uint32_t)lane + 32u < len[u] ? (uint32_t)__ldg(src + lane + 32) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        if ((uint32_t)lane < len[u]) nn[(size_t)b[u] + lane] = lo[u];
+        if ((uint32_t)lane + 32u < len[u]) nn[(size_t)b[u] + lane + 32] = hi[u];
+    }
 }
 
 int pgeof_radius_search_csr_dev(const float* data, size_t n_data, const float* query, size_t n_query, float search_radius,
@@ -626,12 +643,9 @@ int pgeof_radius_search_csr_dev(const float* data, size_t n_data, const float* q
         PGEOF_CUDA(cudaMemsetAsync(nn_ptr, 0, (n_query + 1) * sizeof(uint32_t), s));
         if (n_query && max_knn) {
             if (single) {
-                DeviceBuffer d2;
+                // the search writes every row's count into nn_ptr and its hits into the parked table (SearchArgs::nn_ptr)
                 PGEOF_TRY(pend.idx.alloc(n_query * (size_t)max_knn * 4, s));
-                PGEOF_TRY(d2.alloc(n_query * (size_t)max_knn * 4, s));
-                PGEOF_TRY(search_run(SEARCH_RADIUS, data, n_data, query, n_query, max_knn, search_radius, pend.idx.ptr, d2.as<float>(), nullptr, s));
-                padded_row_count_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, s>>>(pend.idx.as<int32_t>(), n_query, max_knn, nn_ptr);
-                PGEOF_LAUNCH_CHECK();
+                PGEOF_TRY(search_run(SEARCH_RADIUS, data, n_data, query, n_query, max_knn, search_radius, pend.idx.ptr, nullptr, nn_ptr, s));
                 pend.data = data; pend.query = query; pend.n_data = n_data; pend.n_query = n_query; pend.radius = search_radius;
                 pend.max_knn = max_knn; pend.nn_ptr = nn_ptr; pend.device = dev;
             } else {
@@ -651,7 +665,8 @@ int pgeof_radius_search_csr_dev(const float* data, size_t n_data, const float* q
                         pend.radius == search_radius && pend.max_knn == max_knn && pend.nn_ptr == nn_ptr && pend.device == dev &&
                         pend.idx.stream == s;
     if (parked) {   // call 2 of the pair: compact the parked table
-        padded_compact_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, s>>>(pend.idx.as<int32_t>(), n_query, max_knn, nn_ptr, nn);
+        if (max_knn <= 64) padded_compact8_kernel<<<(unsigned)((n_query + 63) / 64), 256, 0, s>>>(pend.idx.as<int32_t>(), n_query, max_knn, nn_ptr, nn);
+        else padded_compact_kernel<<<(unsigned)((n_query + 7) / 8), 256, 0, s>>>(pend.idx.as<int32_t>(), n_query, max_knn, nn_ptr, nn);
         PGEOF_LAUNCH_CHECK();
         pend.clear();
         return PGEOF_OK;

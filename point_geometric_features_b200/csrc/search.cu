@@ -68,7 +68,8 @@ struct SearchArgs {
     float target;            // kNN: candidate count the seeded ball should hold
     void* indices;           // uint32 (knn) / int32 (radius) dense rows, or CSR nn
     float* sqr_dist;
-    uint32_t* nn_ptr;        // RADIUS_COUNT: per-row counts out; RADIUS_CSR: row offsets in
+    uint32_t* nn_ptr;        // RADIUS_COUNT: per-row counts out; RADIUS_CSR: row offsets in; RADIUS with nn_ptr set: counts out AND
+                             // the padded index rows hold their hits only (no -1 padding, no distances): the single-search CSR pair
     unsigned long long* stats;   // optional tile-kernel counters (PGEOF_KNN_STATS=1), else null
     uint32_t flags;          // debugging switches (PGEOF_KNN_FLAGS): 1 = volume-only radius seed, 2 = no radius retries
     uint2* slow_list;        // tile kernel: (query position, bits(radius hint)) of the queries left to knn_slow_kernel
@@ -274,6 +275,15 @@ __device__ __forceinline__ void search_one(const GridView& g, const SearchArgs& 
         write_knn_row<M>(a, row, k, v, lane);
     } else if (MODE == SEARCH_RADIUS) {
         int32_t* idx = reinterpret_cast<int32_t*>(a.indices) + (size_t)row * k;
+        if (a.nn_ptr) {                                    // single-search CSR pair: the count + the hits, nothing else
+            if (lane == 0) a.nn_ptr[row] = need;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const uint32_t e = m * 32 + lane;
+                if (e < need) idx[e] = (int32_t)key_idx(v[m]);
+            }
+            return;
+        }
         float* d2 = a.sqr_dist + (size_t)row * k;
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -807,6 +817,25 @@ __global__ void __launch_bounds__(NWARPS * 32) knn_tile_kernel(const GridView g,
             const uint32_t* plane_d = list;
             const uint32_t* plane_i = reinterpret_cast<const uint32_t*>(stage);
             const unsigned okm = __ballot_sync(kFull, ok);
+            if (MODE == SEARCH_RADIUS && a.nn_ptr) {
+                // single-search CSR pair (radius_search_csr): the row's count goes straight into the offsets array and only
+                // the hits are written -- no -1 / 0 padding, no distances (the padded table is scratch, compacted afterwards)
+                if (ok) a.nn_ptr[row] = need;
+#pragma unroll 8
+                for (int q = 0; q < 32; ++q) {
+                    const uint32_t rowq = __shfl_sync(kFull, row, q);
+                    const uint32_t needq = ((okm >> q) & 1u) ? __shfl_sync(kFull, need, q) : 0u;
+                    uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)rowq * k + lane;
+#pragma unroll
+                    for (int r = 0; r < M; ++r) {
+                        const uint32_t e = r * 32 + lane;
+                        uint32_t vi;
+                        if (SLOTS) vi = __float_as_uint(stage[reinterpret_cast<const uint16_t*>(list + NOUT * S)[e * PS + q]].w);
+                        else vi = plane_i[e * S + q];
+                        if (e < needq) idx[r * 32] = vi;
+                    }
+                }
+            } else
             // branch free: predicated stores, one 64-bit row offset per row
 #pragma unroll 8
             for (int q = 0; q < 32; ++q) {
@@ -1454,6 +1483,10 @@ __global__ void __launch_bounds__(kBigThreads) search_big_kernel(const GridView 
             uint32_t* idx = reinterpret_cast<uint32_t*>(a.indices) + (size_t)row * k;
             float* d2 = a.sqr_dist + (size_t)row * k;
             for (uint32_t e = threadIdx.x; e < k; e += kBigThreads) { idx[e] = key_idx(buf[e]); d2[e] = key_d2(buf[e]); }
+        } else if (MODE == SEARCH_RADIUS && a.nn_ptr) {                    // single-search CSR pair: the count + the hits
+            int32_t* idx = reinterpret_cast<int32_t*>(a.indices) + (size_t)row * k;
+            if (threadIdx.x == 0) a.nn_ptr[row] = need;
+            for (uint32_t e = threadIdx.x; e < need; e += kBigThreads) idx[e] = (int32_t)key_idx(buf[e]);
         } else if (MODE == SEARCH_RADIUS) {
             int32_t* idx = reinterpret_cast<int32_t*>(a.indices) + (size_t)row * k;
             float* d2 = a.sqr_dist + (size_t)row * k;
