@@ -257,6 +257,63 @@ __global__ void __launch_bounds__(kMsThreads, 3) multiscale_direct_kernel(const 
     for (; s < a.n_scales_pass; ++s) store11(out + s * 11, zero);
 }
 
+// compute_features_multiscale in two passes.  The kernel above waits on its gathers (ncu r2ab_ms: long_scoreboard 6 stalled
+// warps per issue) while 73 % of its instructions are the eigen solves, which its 80 registers pay for with a quarter less
+// occupancy: gathering and solving do not overlap well inside one thread.  Pass 1 is the walker alone (moments only, 32 warps
+// per SM) and parks the nine prefix moments of every (row, scale) in scratch (36 B); pass 2 is one thread per (row, scale):
+// load, solve, 11 formulas, store -- no gathers, no divergence between scales.  Same operations on the same values as the
+// one-pass kernel: bit identical.  Scratch: 36 B x rows x scales per chunk of rows (<= 1.5 GB).
+__global__ void __launch_bounds__(kMsThreads, 4) multiscale_moments_kernel(const FeatArgs a, float* __restrict__ mom, uint32_t pos0, uint32_t pos1)
+{
+    const uint32_t pos = pos0 + blockIdx.x * kMsThreads + threadIdx.x;      // position in the (spatially ordered) row sequence
+    if (pos >= pos1) return;
+    const uint32_t row = a.order ? __ldg(a.order + pos) : pos;
+    float* const dst = mom + (size_t)(pos - pos0) * a.n_scales_pass * 9;
+    unsigned long long b, e;
+    row_span(a, row, b, e);
+    if (e < b || e > a.nnz || b < a.nn_lo || e - b > 0xffffffffull) { atomicExch(a.err, 1); return; }
+    const uint32_t len = (uint32_t)(e - b);
+    uint32_t n_fit = 0, s = 0;
+    while (n_fit < a.n_scales_pass && a.scales[n_fit] <= len) ++n_fit;
+    if (!n_fit || a.scales[n_fit - 1] == 0) return;
+    while (s < n_fit && a.scales[s] == 0) ++s;
+    Moments m;
+    uint32_t next_k = s < n_fit ? a.scales[s] : 0xffffffffu;
+    auto acc = [&](uint32_t j, float dx, float dy, float dz) {
+        m.add(dx, dy, dz);
+        while (j + 1 == next_k) {
+            float* d = dst + s * 9;
+            d[0] = m.sx; d[1] = m.sy; d[2] = m.sz; d[3] = m.sxx; d[4] = m.sxy; d[5] = m.sxz; d[6] = m.syy; d[7] = m.syz; d[8] = m.szz;
+            ++s;
+            next_k = s < n_fit ? a.scales[s] : 0xffffffffu;
+        }
+    };
+    if (!walk_direct(a, b, a.scales[n_fit - 1], acc)) atomicExch(a.err, 2);
+}
+
+__global__ void __launch_bounds__(256) multiscale_eigen_kernel(const FeatArgs a, const float* __restrict__ mom, uint32_t pos0, uint32_t pos1)
+{
+    const size_t item = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const uint32_t rel = (uint32_t)(item / a.n_scales_pass), s = (uint32_t)(item - (size_t)rel * a.n_scales_pass);
+    if (rel >= pos1 - pos0) return;
+    const uint32_t pos = pos0 + rel;
+    const uint32_t row = a.order ? __ldg(a.order + pos) : pos;
+    float f[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) f[i] = 0.f;
+    unsigned long long b, e;
+    row_span(a, row, b, e);
+    const uint32_t k = a.scales[s];
+    if (!(e < b || e > a.nnz || b < a.nn_lo || e - b > 0xffffffffull) && k > 0 && k <= e - b && *reinterpret_cast<volatile int*>(a.err) == 0) {
+        const float* src = mom + item * 9;                                   // pgeof.hpp:175,193: rows too short for a scale stay 0
+        Moments m;
+        m.sx = __ldg(src); m.sy = __ldg(src + 1); m.sz = __ldg(src + 2); m.sxx = __ldg(src + 3); m.sxy = __ldg(src + 4); m.sxz = __ldg(src + 5);
+        m.syy = __ldg(src + 6); m.syz = __ldg(src + 7); m.szz = __ldg(src + 8);
+        features11<float>(m.pca(k, a.eig_order), f);
+    }
+    store11(a.out + ((size_t)row * a.n_scales_total + a.scale_base + s) * 11, f);
+}
+
 // compute_features_optimal on the direct walker.  Prefix moments in double as in optimal_kernel; the entropy of every
 // candidate size is first evaluated in FLOAT from Jacobi eigenvalues (accurate to a few ulp of the matrix norm for
 // every eigenvalue, so the float and double entropies differ by < 3e-5 in the worst case, ~1e-6 typically).  A
@@ -783,8 +840,23 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
         a.n_scales_pass = (uint32_t)std::min<size_t>(kMaxScalesPerPass, n_scales - base);
         for (uint32_t s = 0; s < a.n_scales_pass; ++s) a.scales[s] = k_scales_host[base + s];
         KernelTimer timer("multiscale", stream);
+        // PGEOF_MULTISCALE_SPLIT = 0: the one-pass kernel (kept as an A/B switch)
+        if (env_int("PGEOF_MULTISCALE_SPLIT", 1) != 0) {
+            const size_t per_row = (size_t)a.n_scales_pass * 9 * sizeof(float);
+            const size_t chunk = std::max<size_t>(1, std::min<size_t>(n_rows, (size_t(3) << 29) / per_row));
+            DeviceBuffer mom;
+            PGEOF_TRY(mom.alloc(chunk * per_row, stream));
+            for (size_t r0 = 0; r0 < n_rows; r0 += chunk) {
+                const size_t r1 = std::min(n_rows, r0 + chunk);
+                multiscale_moments_kernel<<<(unsigned)((r1 - r0 + kMsThreads - 1) / kMsThreads), kMsThreads, 0, stream>>>(a, mom.as<float>(), (uint32_t)r0, (uint32_t)r1);
+                PGEOF_LAUNCH_CHECK();
+                multiscale_eigen_kernel<<<(unsigned)(((r1 - r0) * a.n_scales_pass + 255) / 256), 256, 0, stream>>>(a, mom.as<float>(), (uint32_t)r0, (uint32_t)r1);
+                PGEOF_LAUNCH_CHECK();
+            }
+        } else {
         multiscale_direct_kernel<<<(unsigned)((n_rows + kMsThreads - 1) / kMsThreads), kMsThreads, 0, stream>>>(a);
         PGEOF_LAUNCH_CHECK();
+        }
     }
     return device_flag_check(err.as<int>(), stream, "compute_features_multiscale");
 }
