@@ -40,6 +40,7 @@ constexpr int kMaxScalesPerPass = 8;
 struct FeatArgs {
     uint32_t n_xyz;
     const float4* pts;            // the cloud as 16-B float4 records (input order): one LDG.128 per gather
+    cudaTextureObject_t tex;      // the same records behind a 1-D linear texture (0: none): the gathers of the walkers go through the TEX pipe
     const uint32_t* order;        // spatial row permutation, or nullptr = identity
     const uint32_t* nn; unsigned long long nnz;
     unsigned long long nn_lo;              // rows may only address nn[nn_lo, nnz): a host pipeline hands the kernels one slice of nn at a time
@@ -117,6 +118,16 @@ __device__ __forceinline__ void row_span(const FeatArgs& a, uint32_t row, unsign
     else { b = __ldg(a.nn_ptr + row); e = __ldg(a.nn_ptr + row + 1); }
 }
 
+// one gathered point: through the texture units when the call made a texture of the cloud.  A warp's 32 scattered 16-byte
+// records are 32 wavefronts of the LSU data pipe, which the gather kernels run at 60-74 % of; as texels they cost the
+// feature / multiscale / optimal kernels 2 / 5 / 5 % less time (alternating the two pipes: 7 % MORE -- what the gathers wait
+// for is the miss path behind L1, not a pipe; profiles/r2_summary.md).  PGEOF_FEATURES_TEX = 0 keeps the LDG path.
+__device__ __forceinline__ float4 fetch_pt(const FeatArgs& a, uint32_t i)
+{
+    if (a.tex) return tex1Dfetch<float4>(a.tex, (int)i);
+    return __ldg(a.pts + i);
+}
+
 // up to N (<= 7) consecutive entries: indices first, then their gathers together, then the moments in order
 template <int N, typename Acc>
 __device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __restrict__ p, uint32_t j0, uint32_t cnt, uint32_t i0, const float4& o,
@@ -130,7 +141,7 @@ __device__ __forceinline__ void walk_some(const FeatArgs& a, const uint32_t* __r
         if (i[u] >= a.n_xyz) { ok = false; i[u] = i0; }
     }
 #pragma unroll
-    for (int u = 0; u < N; ++u) q[u] = __ldg(a.pts + i[u]);
+    for (int u = 0; u < N; ++u) q[u] = fetch_pt(a, i[u]);
 #pragma unroll
     for (int u = 0; u < N; ++u) if ((uint32_t)u < cnt) acc(j0 + u, q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
 }
@@ -143,7 +154,7 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, unsigned long lon
     const uint32_t n = a.n_xyz;
     const uint32_t i0 = __ldg(p);
     if (i0 >= n) return false;
-    const float4 o = __ldg(a.pts + i0);   // origin of the shifted moments; its own term is zero
+    const float4 o = fetch_pt(a, i0);   // origin of the shifted moments; its own term is zero
     bool ok = true;
     acc(0u, 0.f, 0.f, 0.f);
     uint32_t j = 1;
@@ -157,7 +168,7 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, unsigned long lon
 #pragma unroll
         for (int u = 0; u < 8; ++u) if (i[u] >= n) { ok = false; i[u] = i0; }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) q[u] = __ldg(a.pts + i[u]);
+        for (int u = 0; u < 8; ++u) q[u] = fetch_pt(a, i[u]);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc(j + u, q[u].x - o.x, q[u].y - o.y, q[u].z - o.z);
     }
@@ -494,7 +505,7 @@ __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArg
             if (eligible && !ok) atomicExch(a.err, 2);
             if (eligible && ok) {
                 const uint32_t k0 = min(max(max(a.k_min, a.k_min_search), 1u), len);    // :274
-                const float4 o = __ldg(a.pts + i0);
+                const float4 o = fetch_pt(a, i0);
                 MomentsD m;
                 double best_c[6] = {0, 0, 0, 0, 0, 0}, best_h64 = 0.0;
                 float best_h32 = 0.f, best_err = 0.f;
@@ -518,7 +529,7 @@ __global__ void __launch_bounds__(kRows, MINB) optimal_scan_kernel(const FeatArg
                     for (int u = 0; u < 8; ++u) if (i[u] >= a.n_xyz) { ok = false; i[u] = i0; }
                     float4 q[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) q[u] = __ldg(a.pts + i[u]);
+                    for (int u = 0; u < 8; ++u) q[u] = fetch_pt(a, i[u]);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
                         sd[(3 * u + 0) * kRows] = q[u].x - o.x; sd[(3 * u + 1) * kRows] = q[u].y - o.y; sd[(3 * u + 2) * kRows] = q[u].z - o.z;
@@ -736,6 +747,8 @@ int make_args(FeatArgs* a, size_t n_xyz, const uint32_t* nn, size_t nnz, RowPtr 
 // Device buffers of the pre-passes; they live until the feature kernel was enqueued (stream-ordered frees).
 struct Prepass {
     DeviceBuffer pts, order;
+    cudaTextureObject_t tex = 0;
+    ~Prepass() { if (tex) cudaDestroyTextureObject(tex); }
 };
 
 // PGEOF_FEATURES_SORT = 0 keeps the rows in input order (debugging; small inputs do that anyway)
@@ -748,6 +761,18 @@ int prepare(FeatArgs* a, const float* xyz, Prepass* p, cudaStream_t stream)
     if (n) {
         pad_xyz_kernel<<<(n + 255) / 256, 256, 0, stream>>>(xyz, n, p->pts.as<float4>());
         PGEOF_LAUNCH_CHECK();
+    }
+    a->tex = 0;
+    if (n && n <= (1u << 27) && env_int("PGEOF_FEATURES_TEX", 1) != 0) {    // 1-D linear textures hold 2^27 texels
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = p->pts.ptr;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = (size_t)n * sizeof(float4);
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        if (cudaCreateTextureObject(&p->tex, &rd, &td, nullptr) == cudaSuccess) a->tex = p->tex;
+        else { cudaGetLastError(); p->tex = 0; }
     }
     // 2. spatial row order (counting sort by the Morton cell of the first neighbour)
     const int min_rows = env_int("PGEOF_FEATURES_SORT_MIN_ROWS", 32768);
