@@ -10,7 +10,12 @@
  *                       itself on an internal stream of the current device.
  *   pgeof_<fn>_dev      DEVICE buffers (DLPack / torch CUDA tensors) on `stream`
  *                       (a cudaStream_t cast to void*; NULL = legacy default stream).
- *                       Asynchronous with respect to the host except where noted.
+ *                       Work is enqueued on `stream`, but the calls are NOT fully asynchronous:
+ *                       every search synchronises the stream once or twice (bounding box -> grid
+ *                       dimensions on the host, count of the queries handed to a second pass) and every
+ *                       feature call once at its end (the bad-index flag that becomes PGEOF_EINDEX), so
+ *                       results are complete and errors reported when a call returns; do not capture
+ *                       them in a CUDA graph ("Host synchronisation").
  *
  * Conventions
  *   - all arrays are dense C-contiguous; xyz-like arrays are (n,3) row-major.
