@@ -105,6 +105,28 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(GridView g, const flo
     out[pos] = make_float4(x, y, z, __uint_as_float((uint32_t)i));
 }
 
+// The scatter in two steps: 16-byte records written to random places of a 160 MB array (10 M points) leave L2 as half-written
+// sectors; a 4-byte permutation (40 MB, stays in L2) written at random and a second pass that READS the cloud at random
+// (120 MB, in L2 from the count pass) and WRITES the records in order moves the same data with coalesced stores.
+__global__ void __launch_bounds__(kThreads) perm_kernel(GridView g, const float* __restrict__ xyz, size_t n, const uint32_t* __restrict__ cell_start,
+                                                        const uint32_t* __restrict__ rank, uint32_t* __restrict__ perm, int use_clip)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    if (use_clip && !inside_clip(g, x, y, z)) return;
+    perm[__ldg(cell_start + cell_index(g, x, y, z)) + __ldg(rank + i)] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(kThreads) gather_sorted_kernel(const float* __restrict__ xyz, size_t n, const uint32_t* __restrict__ perm,
+                                                                 const uint32_t* __restrict__ total, float4* __restrict__ out)
+{
+    const size_t pos = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n || pos >= __ldg(total)) return;               // a clipped grid indexes fewer than n points
+    const uint32_t i = __ldg(perm + pos);
+    out[pos] = make_float4(__ldg(xyz + 3 * (size_t)i), __ldg(xyz + 3 * (size_t)i + 1), __ldg(xyz + 3 * (size_t)i + 2), __uint_as_float(i));
+}
+
 // ---------------------------------------------------------------------------
 // exclusive scan, three passes: tile sums -> scan of tile sums -> rescan + offset
 // ---------------------------------------------------------------------------
@@ -332,8 +354,18 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
     // 4. scan -> scatter
     PGEOF_TRY(out->pts.alloc(n * sizeof(float4), stream));
     PGEOF_TRY(exclusive_scan_u32(cs, out->n_cells, stream));
+    const char* sc = std::getenv("PGEOF_GRID_SCATTER");    // 1: the one-step scatter (A/B switch)
+    if (!sc || std::atoi(sc) != 1) {
+        DeviceBuffer perm;
+        PGEOF_TRY(perm.alloc(n * sizeof(uint32_t), stream));
+        perm_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), perm.as<uint32_t>(), clip ? 1 : 0);
+        PGEOF_LAUNCH_CHECK();
+        gather_sorted_kernel<<<blocks, kThreads, 0, stream>>>(xyz, n, perm.as<uint32_t>(), cs + out->n_cells, out->pts.as<float4>());
+        PGEOF_LAUNCH_CHECK();
+    } else {
     scatter_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), out->pts.as<float4>(), clip ? 1 : 0);
     PGEOF_LAUNCH_CHECK();
+    }
     g.cell_start = cs;
     g.pts = out->pts.as<float4>();
     return PGEOF_OK;
