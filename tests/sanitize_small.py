@@ -62,5 +62,19 @@ if os.environ.get("SAN_VARIANTS"):
         pgeof.knn_search(big, big[:20000], 100)
         pgeof.compute_features_optimal(big, n100, p100, 1, 1, 10)
         del os.environ[name]
+# last session of round 2: device flavour of the single-search radius CSR pair (rows write their count and hits only), two-pass
+# multiscale, closed-form optimal filter, texture gathers, two-step grid scatter -- and their switched-off counterparts
+tx = torch.from_numpy(xyz).cuda()
+rn, rp = b200.radius_search_csr(tx, tx, 0.5, 32)
+assert (rn.cpu().numpy() == nn).all() and (rp.cpu().numpy() == nn_ptr).all()
+rn2, rp2 = b200.radius_search_csr(tx, tx, 0.8, 100)                       # max_knn > 64: the warp-per-query routine writes the counts
+pgeof.compute_features_multiscale(tx, rn, rp, [2, 4, 8, 16, 32])
+for name, value in (("PGEOF_OPTIMAL_SCAN", "1"), ("PGEOF_MULTISCALE_SPLIT", "0"), ("PGEOF_FEATURES_TEX", "0"), ("PGEOF_GRID_SCATTER", "1"), ("PGEOF_RADIUS_TILE", "0")):
+    os.environ[name] = value
+    pgeof.knn_search(big, big[:20000], 30)
+    b200.radius_search_csr(tx, tx, 0.5, 32)
+    pgeof.compute_features_multiscale(big, n100, p100, [10, 50, 100])
+    pgeof.compute_features_optimal(big, n100, p100, 1, 1, 10)
+    del os.environ[name]
 torch.cuda.synchronize()
 print("sanitize_small round-2 paths ok")
