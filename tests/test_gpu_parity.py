@@ -737,7 +737,7 @@ def test_optimal_k_against_the_float32_arithmetic_of_the_reference():
 
 SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"), ("PGEOF_KNN_TILE128", "1"), ("PGEOF_KNN_TWO_LEVEL", "0"),
             ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0"),
-            ("PGEOF_GRID_SCATTER", "1"), ("PGEOF_MULTISCALE_SPLIT", "0"), ("PGEOF_FEATURES_TEX", "0"), ("PGEOF_OPTIMAL_SCAN", "0"), ("PGEOF_OPTIMAL_SCAN", "1"), ("PGEOF_OPTIMAL_CTAS", "6")]
+            ("PGEOF_GRID_SCATTER", "1"), ("PGEOF_RADIUS_CSR_TWO_PASS", "1"), ("PGEOF_MULTISCALE_SPLIT", "0"), ("PGEOF_FEATURES_TEX", "0"), ("PGEOF_OPTIMAL_SCAN", "0"), ("PGEOF_OPTIMAL_SCAN", "1"), ("PGEOF_OPTIMAL_CTAS", "6")]
 
 
 @pytest.mark.parametrize("name,value", SWITCHES)
@@ -760,7 +760,8 @@ def test_every_switch_leaves_the_results_unchanged(name, value, monkeypatch):
         ms = pgeof.compute_features_multiscale(t, idx.view(-1), ptr, [10, 13, 20, 50])
         op = pgeof.compute_features_optimal(t, idx.view(-1), ptr, 1, 1, 10)
         fu = b200.knn_features(t, 50)
-        got = [x.cpu().numpy().view(np.uint32) for x in (idx, d2, qi, qd, wi, wd, ri, rd, f, ms, op, fu)]
+        cn, cp = b200.radius_search_csr(t, t, 6.0, 40)                               # single-search pair (PGEOF_RADIUS_CSR_TWO_PASS, PGEOF_RADIUS_TILE)
+        got = [x.cpu().numpy().view(np.uint32) for x in (idx, d2, qi, qd, wi, wd, ri, rd, f, ms, op, fu, cn, cp)]
         if phase == "default":
             base = got
             ref = cpu.knn_search(xyz, xyz[:3000], 50)
