@@ -839,9 +839,24 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
         PGEOF_LAUNCH_CHECK();
         return PGEOF_OK;
     };
-    if (cta == 128) { a.tma_out = a.tma_out && ((128 * 11 * 4) % 16 == 0); PGEOF_TRY(launch(features_direct_kernel<128>, 128)); }
-    else if (cta == 256) { a.tma_out = a.tma_out && ((256 * 11 * 4) % 16 == 0); PGEOF_TRY(launch(features_direct_kernel<256>, 256)); }
-    else { a.tma_out = a.tma_out && ((512 * 11 * 4) % 16 == 0); PGEOF_TRY(launch(features_direct_kernel<512>, 512)); }
+    // shared-memory carve-out: the 1024 resident rows stage 48 KB of output rows; everything else should be L1 for the gathers.
+    // Asking for 25 % (the 64 KB configuration) instead of the driver's choice: 2.70 -> 2.63 ms at 10 M x 50 (0 %: the CTAs no
+    // longer fit two per SM, 3.17 ms; 50 %: 2.78 ms).  Also measured and not kept: one CTA of 1024 rows (3.03 ms) and per-thread
+    // 44-byte stores without any staging (3.72 ms).
+    const int carve = env_int("PGEOF_FEATURES_CARVEOUT", 25);
+    if (cta == 128) {
+        a.tma_out = a.tma_out && ((128 * 11 * 4) % 16 == 0);
+        if (carve >= 0) PGEOF_CUDA(cudaFuncSetAttribute(features_direct_kernel<128>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        PGEOF_TRY(launch(features_direct_kernel<128>, 128));
+    } else if (cta == 256) {
+        a.tma_out = a.tma_out && ((256 * 11 * 4) % 16 == 0);
+        if (carve >= 0) PGEOF_CUDA(cudaFuncSetAttribute(features_direct_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        PGEOF_TRY(launch(features_direct_kernel<256>, 256));
+    } else {
+        a.tma_out = a.tma_out && ((512 * 11 * 4) % 16 == 0);
+        if (carve >= 0) PGEOF_CUDA(cudaFuncSetAttribute(features_direct_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        PGEOF_TRY(launch(features_direct_kernel<512>, 512));
+    }
     return device_flag_check(err.as<int>(), stream, "compute_features");
 }
 
