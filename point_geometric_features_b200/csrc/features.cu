@@ -883,7 +883,9 @@ int features_multiscale_run(const float* xyz, size_t n_xyz, const uint32_t* nn, 
         // PGEOF_MULTISCALE_SPLIT = 0: the one-pass kernel (kept as an A/B switch)
         if (env_int("PGEOF_MULTISCALE_SPLIT", 1) != 0) {
             const size_t per_row = (size_t)a.n_scales_pass * 9 * sizeof(float);
-            const size_t chunk = std::max<size_t>(1, std::min<size_t>(n_rows, (size_t(3) << 29) / per_row));
+            size_t chunk = std::max<size_t>(1, std::min<size_t>(n_rows, (size_t(3) << 29) / per_row));
+            const int chunk_rows = env_int("PGEOF_MULTISCALE_CHUNK_ROWS", 0);   // tests: several chunks on a small input
+            if (chunk_rows > 0) chunk = std::min<size_t>(chunk, (size_t)chunk_rows);
             DeviceBuffer mom;
             PGEOF_TRY(mom.alloc(chunk * per_row, stream));
             for (size_t r0 = 0; r0 < n_rows; r0 += chunk) {
