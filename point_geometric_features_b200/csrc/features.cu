@@ -180,11 +180,14 @@ __device__ __forceinline__ bool walk_direct(const FeatArgs& a, unsigned long lon
 // sequence and walks it tile by tile: the rows an SM works on at any time form one or two compact blobs, so a
 // gathered point is re-used out of L1 by the blob's other rows (small independent CTAs spread over the whole
 // in-flight window shared their gathers only through L2).
-template <int THREADS>
+// PHASES = 2: the tile's rows are staged and written half at a time, so two resident CTAs need 25 KB of shared memory instead
+// of 49 KB and the 32 KB carve-out leaves 196 KB of L1 to the gathers
+template <int THREADS, int PHASES = 1>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kernel(const FeatArgs a)
 {
-    __shared__ uint32_t s_rowid[THREADS];
-    __shared__ __align__(128) float s_out[THREADS * 11];   // source of a TMA bulk store: 16-B alignment required
+    constexpr int STAGED = THREADS / PHASES;
+    __shared__ uint32_t s_rowid[STAGED];
+    __shared__ __align__(128) float s_out[STAGED * 11];   // source of a TMA bulk store: 16-B alignment required
     const uint32_t tiles = (a.n_rows + THREADS - 1) / THREADS;
     const uint32_t per = (tiles + gridDim.x - 1) / gridDim.x;
     const uint32_t t_end = min(tiles, (blockIdx.x + 1) * per);
@@ -196,7 +199,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
         for (int i = 0; i < 11; ++i) f[i] = 0.f;
         uint32_t row = r0 + threadIdx.x;
         if (threadIdx.x < t.rows && a.order) row = __ldg(a.order + row);
-        s_rowid[threadIdx.x] = (a.out_rows && threadIdx.x < t.rows) ? __ldg(a.out_rows + row) : row;
+        const uint32_t out_row = (a.out_rows && threadIdx.x < t.rows) ? __ldg(a.out_rows + row) : row;
         if (threadIdx.x < t.rows) {
             unsigned long long b, e;
             row_span(a, row, b, e);
@@ -209,9 +212,18 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) features_direct_kerne
             }
         }
 #pragma unroll
-        for (int i = 0; i < 11; ++i) s_out[threadIdx.x * 11 + i] = f[i];
-        store_rows<11>(a, t, s_out, s_rowid);
-        __syncthreads();                                         // the staging buffers are re-used by the next tile
+        for (int ph = 0; ph < PHASES; ++ph) {
+            if ((int)threadIdx.x / STAGED == ph) {
+                const uint32_t slot = threadIdx.x - ph * STAGED;
+                s_rowid[slot] = out_row;
+#pragma unroll
+                for (int i = 0; i < 11; ++i) s_out[slot * 11 + i] = f[i];
+            }
+            const uint32_t done = ph * STAGED;
+            Tile th{r0 + done, t.rows > done ? min((uint32_t)STAGED, t.rows - done) : 0u, t.bulk_store};
+            store_rows<11>(a, th, s_out, s_rowid);
+            __syncthreads();                                     // the staging buffers are re-used by the next phase / tile
+        }
     }
 }
 
@@ -852,6 +864,10 @@ int features_run(const float* xyz, size_t n_xyz, const uint32_t* nn, size_t nnz,
         a.tma_out = a.tma_out && ((256 * 11 * 4) % 16 == 0);
         if (carve >= 0) PGEOF_CUDA(cudaFuncSetAttribute(features_direct_kernel<256>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
         PGEOF_TRY(launch(features_direct_kernel<256>, 256));
+    } else if (env_int("PGEOF_FEATURES_PHASES", 2) == 2) {     // 2.63 -> 2.60 ms at 10 M x 50 (1: one phase, 64 KB carve-out)
+        a.tma_out = a.tma_out && ((256 * 11 * 4) % 16 == 0);
+        PGEOF_CUDA(cudaFuncSetAttribute(features_direct_kernel<512, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, env_int("PGEOF_FEATURES_CARVEOUT", 14)));
+        PGEOF_TRY(launch(features_direct_kernel<512, 2>, 512));
     } else {
         a.tma_out = a.tma_out && ((512 * 11 * 4) % 16 == 0);
         if (carve >= 0) PGEOF_CUDA(cudaFuncSetAttribute(features_direct_kernel<512>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
