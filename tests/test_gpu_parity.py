@@ -737,7 +737,7 @@ def test_optimal_k_against_the_float32_arithmetic_of_the_reference():
 
 SWITCHES = [("PGEOF_KNN_TILE", "0"), ("PGEOF_RADIUS_TILE", "0"), ("PGEOF_GRID_CLIP", "0"), ("PGEOF_KNN_WARPS", "2"), ("PGEOF_KNN_FUSED", "0"), ("PGEOF_KNN_LOCK", "0"), ("PGEOF_KNN_PAIR", "1"), ("PGEOF_KNN_ROLLED", "1"), ("PGEOF_KNN_TILE128", "1"), ("PGEOF_KNN_TWO_LEVEL", "0"),
             ("PGEOF_FEATURES_SORT", "0"), ("PGEOF_FEATURES_CTA", "128"), ("PGEOF_FEATURES_CTA", "256"), ("PGEOF_FEATURES_SORT_MIN_ROWS", "0"),
-            ("PGEOF_GRID_SCATTER", "1"), ("PGEOF_RADIUS_CSR_TWO_PASS", "1"), ("PGEOF_MULTISCALE_SPLIT", "0"), ("PGEOF_MULTISCALE_CHUNK_ROWS", "7001"), ("PGEOF_FEATURES_TEX", "0"), ("PGEOF_FEATURES_CARVEOUT", "-1"), ("PGEOF_FEATURES_PHASES", "1"), ("PGEOF_OPTIMAL_SCAN", "0"), ("PGEOF_OPTIMAL_SCAN", "1"), ("PGEOF_OPTIMAL_CTAS", "6")]
+            ("PGEOF_GRID_SCATTER", "1"), ("PGEOF_GRID_SCATTER", "2"), ("PGEOF_RADIUS_CSR_TWO_PASS", "1"), ("PGEOF_MULTISCALE_SPLIT", "0"), ("PGEOF_MULTISCALE_CHUNK_ROWS", "7001"), ("PGEOF_FEATURES_TEX", "0"), ("PGEOF_FEATURES_CARVEOUT", "-1"), ("PGEOF_FEATURES_PHASES", "1"), ("PGEOF_OPTIMAL_SCAN", "0"), ("PGEOF_OPTIMAL_SCAN", "1"), ("PGEOF_OPTIMAL_CTAS", "6")]
 
 
 @pytest.mark.parametrize("name,value", SWITCHES)
