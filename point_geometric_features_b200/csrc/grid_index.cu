@@ -359,7 +359,9 @@ int grid_build(const float* xyz, size_t n, float cell_edge, float target_occupan
     // 50 M points: 4.0 -> 4.7 ms -- so larger clouds keep the one-step scatter; PGEOF_GRID_SCATTER = 1 / 2 forces either)
     const char* sc = std::getenv("PGEOF_GRID_SCATTER");
     const int sc_mode = sc ? std::atoi(sc) : 0;
-    if (sc_mode == 2 || (sc_mode != 1 && n * 12 <= ((size_t)160 << 20))) {
+    // (a clipped grid indexes a fraction of the cloud: two passes over all n points cost it more than they save, 0.17 -> 0.20 ms
+    // per rank of an 8-way run)
+    if (sc_mode == 2 || (sc_mode != 1 && !clip && n * 12 <= ((size_t)160 << 20))) {
         DeviceBuffer perm;
         PGEOF_TRY(perm.alloc(n * sizeof(uint32_t), stream));
         perm_kernel<<<blocks, kThreads, 0, stream>>>(g, xyz, n, cs, rank.as<uint32_t>(), perm.as<uint32_t>(), clip ? 1 : 0);
