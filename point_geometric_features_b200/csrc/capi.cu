@@ -581,8 +581,9 @@ int pgeof_radius_search(const float* data, size_t n_data, const float* query, si
 
 // Radius search straight into CSR.  Called twice (the caller allocates nn once the total is known): with nn == NULL it
 // writes the row offsets and returns the total, with nn it writes the neighbours.  ONE search serves both calls: the first
-// runs the padded search into library scratch, counts and scans; the scratch stays parked (per host thread) and the second
-// call only compacts it.  If the second call does not match the parked search (other arguments, other thread) it searches
+// runs the search into a (n_query, max_knn) scratch table -- every row writes its count straight into nn_ptr and its hits
+// only, no padding, no distances -- and scans the counts; the scratch stays parked (per host thread) and the second
+// call only compacts it (8 rows per warp).  If the second call does not match the parked search (other arguments, other thread) it searches
 // again -- same result, one search slower.
 
 __global__ void padded_compact_kernel(const int32_t* __restrict__ idx, size_t n_rows, uint32_t max_knn, const uint32_t* __restrict__ nn_ptr,
